@@ -1,0 +1,196 @@
+/*
+ * streamz_b200 -- C ABI of the B200-native (sm_100a) implementation of StreamZ's data-parallel hot path.
+ *
+ * This is the drop-in boundary.  The reference (Mycoearthdome/StreamZ, crate `streamz_rs`) has no FFI of its own:
+ * its boundary is the public Rust API imported by the CLI at streamz-rs/src/main.rs:13-19.  Every entry point below
+ * names the Rust item (file:line in streamz-rs/src/lib.rs) it replaces; INTEGRATION.md shows the `extern "C"` block
+ * and the wrappers a maintainer adds to keep those Rust signatures.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA, torch or C++ types in any signature;
+ *   - every function returns szb_status (0 = ok) unless it is a pure size query; nothing throws or aborts across
+ *     the ABI; szb_last_error() returns a human-readable message for the calling thread's last failure;
+ *   - "host" entry points take host pointers and do their own H2D/D2H copies on the context's stream;
+ *     "_dev" entry points take device pointers that live on the context's device (allocate with szb_dev_alloc);
+ *   - outputs are caller-allocated; capacities are passed explicitly and SZB_ERR_INVALID is returned when too small;
+ *   - a context owns one CUDA stream and scratch buffers: use it from one thread at a time; a net belongs to a
+ *     context; read-only net calls on different contexts are independent;
+ *   - there is NO CPU fallback: without a usable CUDA device szb_ctx_create fails with SZB_ERR_NO_DEVICE.
+ */
+#ifndef STREAMZ_B200_H
+#define STREAMZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lib.rs:25-36 */
+#define SZB_SAMPLE_RATE 44100u /* DEFAULT_SAMPLE_RATE */
+#define SZB_WINDOW_SIZE 800u   /* WINDOW_SIZE */
+#define SZB_HOP_SIZE 400u      /* WINDOW_SIZE / 2, lib.rs:288 */
+#define SZB_N_MELS 26u         /* N_MELS */
+#define SZB_MFCC_SIZE 20u      /* MFCC_SIZE */
+#define SZB_FEATURE_SIZE 60u   /* FEATURE_SIZE (WITH_DELTAS) */
+#define SZB_DEFAULT_DROPOUT 0.2f
+#define SZB_RESAMPLE_TAPS 16u
+
+typedef int32_t szb_status;
+enum {
+    SZB_OK = 0,
+    SZB_ERR_INVALID = 1,     /* bad argument / capacity too small / shape mismatch */
+    SZB_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+    SZB_ERR_NO_DEVICE = 3,   /* no usable sm_100 device: there is no CPU fallback */
+    SZB_ERR_ALLOC = 4,
+    SZB_ERR_NCCL = 5,
+    SZB_ERR_IO = 6,          /* file missing / malformed npy or npz */
+    SZB_ERR_UNSUPPORTED = 7
+};
+
+typedef struct szb_ctx szb_ctx;
+typedef struct szb_net szb_net;
+
+/* ---- library / context ------------------------------------------------------------------------------------------ */
+const char* szb_version(void);
+const char* szb_last_error(void);
+/* One context per (thread, device).  `stream` may be NULL (the context creates its own non-blocking stream) or an
+ * existing cudaStream_t passed as void* (the context then launches on it and does not destroy it). */
+szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out);
+void szb_ctx_destroy(szb_ctx* ctx);
+szb_status szb_ctx_sync(szb_ctx* ctx);
+int32_t szb_ctx_sm_count(const szb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
+uint64_t szb_ctx_launch_count(const szb_ctx* ctx);
+/* Device-time of the work enqueued between start and stop on the context's stream (CUDA events). */
+szb_status szb_timer_start(szb_ctx* ctx);
+szb_status szb_timer_stop(szb_ctx* ctx, float* elapsed_ms);
+/* Accumulated device time (ms) and launches of the dominant extraction kernel since the last reset, measured with
+ * CUDA events around each launch when enabled (used for the roofline figure; off by default). */
+szb_status szb_kernel_timing(szb_ctx* ctx, int32_t enable);
+szb_status szb_kernel_timing_read(szb_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset);
+
+/* device memory helpers for FFI hosts that have no CUDA binding of their own */
+szb_status szb_dev_alloc(szb_ctx* ctx, size_t bytes, void** dptr);
+szb_status szb_dev_free(szb_ctx* ctx, void* dptr);
+szb_status szb_memcpy_h2d(szb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+szb_status szb_memcpy_d2h(szb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+szb_status szb_host_alloc_pinned(size_t bytes, void** hptr);
+szb_status szb_host_free_pinned(void* hptr);
+
+/* ---- tables (FeatureExtractor::new, lib.rs:239-257) --------------------------------------------------------------- */
+/* 26 x 401 mel bank as the reference holds it (f32), 20 x 26 DCT-II rows, polyphase taps [L][16] for `rate`. */
+szb_status szb_table_mel(float* out_26x401);
+szb_status szb_table_dct(float* out_20x26);
+szb_status szb_table_resample_taps(uint32_t rate, float* out /* may be NULL */, uint32_t* L, uint32_t* M);
+
+/* ---- front end ---------------------------------------------------------------------------------------------------- */
+/* n = floor((len - 800) / 400) + 1, or 0 when len < 800 (lib.rs:289-291, 317). */
+uint64_t szb_num_windows(uint64_t n_samples);
+/* floor(n_in * 44100 / rate) (lib.rs:196). */
+uint64_t szb_resample_out_len(uint64_t n_in, uint32_t rate);
+
+/* downmix_to_mono (lib.rs:172-183): interleaved i16 -> mono, i32 sum / channels truncating toward zero. */
+szb_status szb_downmix_to_mono(szb_ctx* ctx, const int16_t* interleaved, uint64_t n_samples, uint32_t channels,
+                               int16_t* mono, uint64_t mono_cap, uint64_t* n_mono);
+
+/* resample_to_44100 (lib.rs:186-209).  rate == 44100 copies.  Otherwise polyphase FIR (DESIGN.md "Resampler"),
+ * output clamped to [-32768, 32767] and truncated toward zero like lib.rs:205-208. */
+szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in, uint32_t rate, int16_t* out,
+                                 uint64_t out_cap, uint64_t* n_out);
+
+/* FeatureExtractor::extract (lib.rs:261-263 -> 279-345): mono i16 @ 44.1 kHz -> [n][60] normalised MFCC+d+dd.
+ * len < 800 gives n = 0 and SZB_OK (lib.rs:289). */
+szb_status szb_extract(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, float* feats, uint64_t cap_windows,
+                       uint64_t* n_windows);
+
+/* Batched form of the rayon loop at main.rs:500-508 (+ batch_resample, lib.rs:541-547, when rate != 44100):
+ * clip c is pcm[clip_off[c] .. clip_off[c+1]) at `rate` Hz; its windows land at feats[win_off[c] .. win_off[c+1]).
+ * win_off has n_clips + 1 entries and is written by the call.  With rate != 44100 the resampler runs fused in front
+ * of the framing (the 44.1 kHz i16 signal -- identical to szb_resample_to_44100's -- never leaves the chip). */
+szb_status szb_extract_batch(szb_ctx* ctx, const int16_t* pcm, const uint64_t* clip_off, uint32_t n_clips,
+                             uint32_t rate, float* feats, uint64_t cap_windows, uint64_t* win_off);
+/* Same with pcm and feats resident on the device; clip_off / win_off stay host arrays. */
+szb_status szb_extract_batch_dev(szb_ctx* ctx, const int16_t* d_pcm, const uint64_t* clip_off, uint32_t n_clips,
+                                 uint32_t rate, float* d_feats, uint64_t cap_windows, uint64_t* win_off);
+/* Total windows the batch will produce (size query for the two calls above). */
+uint64_t szb_extract_batch_windows(const uint64_t* clip_off, uint32_t n_clips, uint32_t rate);
+
+/* ---- SimpleNeuralNet (lib.rs:745-1060) ----------------------------------------------------------------------------- */
+/* SimpleNeuralNet::new (lib.rs:767-790): weights U(-0.5, 0.5), zero biases.  The reference draws from an unseeded
+ * thread_rng; here the stream is a documented counter RNG keyed by `seed`. */
+szb_status szb_net_create(szb_ctx* ctx, uint32_t n_in, uint32_t h1, uint32_t h2, uint32_t n_out, uint64_t seed,
+                          szb_net** out);
+/* Row-major w1[n_in][h1] b1[h1] w2[h1][h2] b2[h2] w3[h2][n_out] b3[n_out] (lib.rs:746-751). */
+szb_status szb_net_from_weights(szb_ctx* ctx, uint32_t n_in, uint32_t h1, uint32_t h2, uint32_t n_out,
+                                const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                                const float* b3, szb_net** out);
+szb_status szb_net_get_weights(szb_net* net, float* w1, float* b1, float* w2, float* b2, float* w3, float* b3);
+szb_status szb_net_dims(const szb_net* net, uint32_t dims[4]);
+/* output_size (lib.rs:792) */
+uint32_t szb_net_output_size(const szb_net* net);
+/* add_output_class (lib.rs:797-821): w3 gains a column (given, or U(-0.5,0.5) from `seed` when NULL), b3 a zero. */
+szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t seed);
+void szb_net_destroy(szb_net* net);
+/* record_training_file / file_lists (lib.rs:855-867): host-side bookkeeping saved into model.npz as
+ * speaker_<i>_files.  szb_net_file_list returns the newline-joined list of `speaker` (len excludes the NUL). */
+szb_status szb_net_record_training_file(szb_net* net, uint32_t speaker, const char* path);
+szb_status szb_net_file_list(const szb_net* net, uint32_t speaker, char* out, size_t cap, size_t* len);
+
+/* forward (lib.rs:880-891), batched: x [B][n_in] -> probs [B][n_out]. */
+szb_status szb_net_forward(szb_net* net, const float* x, uint64_t B, float* probs);
+szb_status szb_net_forward_dev(szb_net* net, const float* d_x, uint64_t B, float* d_probs);
+
+/* train_batch (lib.rs:1002-1060): one mean-gradient SGD step; `target` is ONE [n_out] vector shared by the batch,
+ * exactly the reference's signature.  B == 0 is a no-op. */
+szb_status szb_net_train_batch(szb_net* net, const float* x, uint64_t B, const float* target, float lr);
+/* Superset: per-window labels (label >= n_out -> all-zero target, lib.rs:592-595), optional dropout decisions
+ * keep[B][n_in] (0 = zero the input, lib.rs:119-129), windows left all-zero are skipped and excluded from the
+ * divisor (lib.rs:607-609, 1047).  loss_sum / n_used (may be NULL) return the summed -ln(max(p[label],1e-12)) computed
+ * with the pre-update weights (lib.rs:610-617) and the number of windows used. */
+szb_status szb_net_train_batch_labels(szb_net* net, const float* x, const uint32_t* labels, uint64_t B, float lr,
+                                      const uint8_t* keep, double* loss_sum, uint64_t* n_used);
+/* One epoch of pretrain_from_features' loop (lib.rs:599-622) with the features resident on the device: rows are
+ * visited in the order perm[0..n_perm) (host array; the shuffle of lib.rs:601), in chunks of `batch`.  Dropout
+ * decisions come from d_keep [n][n_in] when non-NULL, else from the counter RNG (seed, stream) when dropout > 0. */
+szb_status szb_net_train_epoch_dev(szb_net* net, const float* d_feats, const uint32_t* d_labels, uint64_t n,
+                                   const uint32_t* perm, uint64_t n_perm, uint32_t batch, float lr, float dropout,
+                                   uint64_t seed, uint64_t stream, const uint8_t* d_keep, double* loss_sum,
+                                   uint64_t* n_used);
+/* The dropout stream above, on the host, for callers that need the decisions (tests, oracle): keep[n_rows][n_in]. */
+szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t* rows, uint64_t n_rows, uint32_t n_in,
+                                 float prob, uint8_t* keep);
+
+/* ---- aggregation (lib.rs:1285-1411) -------------------------------------------------------------------------------- */
+/* Per-class count of windows whose LAST-index argmax probability is >= threshold (lib.rs:1391-1402). */
+szb_status szb_identify_counts(szb_net* net, const float* feats, uint64_t n_windows, float threshold,
+                               uint64_t* counts /* [n_out] */);
+szb_status szb_identify_counts_dev(szb_net* net, const float* d_feats, uint64_t n_windows, float threshold,
+                                   uint64_t* counts /* host [n_out] */);
+/* Per-class sum of window probabilities (lib.rs:1290-1297, 1319-1328). */
+szb_status szb_identify_sums(szb_net* net, const float* feats, uint64_t n_windows, float* sums /* [n_out] */);
+/* identify_speaker_list (lib.rs:1383-1411): extraction + forward + histogram + stable sort by count descending. */
+szb_status szb_identify_speaker_list(szb_net* net, const int16_t* pcm, uint64_t n_samples, float threshold,
+                                     uint32_t* speakers, uint32_t cap, uint32_t* n_speakers);
+
+/* ---- multi-GPU: batch-parallel training, one NCCL all-reduce of the flattened gradient per step --------------------- */
+szb_status szb_comm_unique_id(uint8_t id[128]);
+szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+szb_status szb_comm_destroy(szb_ctx* ctx);
+int32_t szb_comm_world(const szb_ctx* ctx);
+
+/* ---- on-disk formats (host code) ----------------------------------------------------------------------------------- */
+/* feature_cache/<sanitised path>.npy (lib.rs:550-579): C-order <f4 [n][60]. */
+szb_status szb_feature_cache_path(const char* audio_path, char* out, size_t cap);
+szb_status szb_npy_write_f32(const char* path, const float* data, uint64_t rows, uint64_t cols);
+szb_status szb_npy_read_f32(const char* path, float* data, uint64_t cap_elems, uint64_t* rows, uint64_t* cols);
+/* model.npz (lib.rs:1081-1282): stored (uncompressed) zip of npy members w1 b1 w2 b2 sample_rate bits num_speakers
+ * w3_k b3_k (k = 1..C, one column each) speaker_i_files.  Loader also accepts the legacy dense w3 / b3 pair. */
+szb_status szb_net_save(szb_net* net, const char* path, uint32_t sample_rate, uint32_t bits);
+szb_status szb_net_load(szb_ctx* ctx, const char* path, szb_net** out, uint32_t* sample_rate, uint32_t* bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMZ_B200_H */

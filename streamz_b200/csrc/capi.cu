@@ -1,0 +1,420 @@
+// C-ABI layer: context management, tables, and the front-end entry points of include/streamz_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+#include "frontend.cuh"
+#include "tables.hpp"
+
+namespace szb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+szb_status DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return SZB_OK;
+    release();
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        cap = 0;
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return SZB_ERR_ALLOC;
+    }
+    cap = want;
+    return SZB_OK;
+}
+void DevBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+szb_status PinnedBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return SZB_OK;
+    release();
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        cap = 0;
+        set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        return SZB_ERR_ALLOC;
+    }
+    cap = want;
+    return SZB_OK;
+}
+void PinnedBuf::release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+static szb_status drain_ktime(szb_ctx* ctx) {
+    for (auto& pr : ctx->ktime_pending) {
+        SZB_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        SZB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        ctx->ktime_ms += ms;
+        ctx->ktime_launches += 1;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->ktime_pending.clear();
+    return SZB_OK;
+}
+
+// Window offsets of a batch; clips are at `rate` Hz (resampled length floor(n * 44100 / rate), lib.rs:196).
+static void batch_layout(const uint64_t* clip_off, uint32_t n_clips, uint32_t rate, std::vector<uint64_t>& off44,
+                         std::vector<uint64_t>& win_off) {
+    off44.resize(size_t(n_clips) + 1);
+    win_off.resize(size_t(n_clips) + 1);
+    off44[0] = 0;
+    win_off[0] = 0;
+    for (uint32_t c = 0; c < n_clips; ++c) {
+        const uint64_t n_in = clip_off[c + 1] - clip_off[c];
+        const uint64_t n44 = rate == SZB_SAMPLE_RATE ? n_in : szb_resample_out_len(n_in, rate);
+        // resampled clips are laid out back to back, each start rounded up to 8 samples (16-byte aligned rows)
+        off44[c + 1] = rate == SZB_SAMPLE_RATE ? clip_off[c + 1] - clip_off[0] : ((off44[c] + n44 + 7) & ~uint64_t(7));
+        win_off[c + 1] = win_off[c] + szb_num_windows(n44);
+    }
+}
+
+}  // namespace szb
+
+using namespace szb;
+
+extern "C" {
+
+const char* szb_version(void) { return "streamz_b200 0.1.0 (sm_100a)"; }
+const char* szb_last_error(void) { return g_last_error.c_str(); }
+
+szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
+    SZB_REQUIRE(out != nullptr, "szb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        set_error("no CUDA device available (%s); streamz_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return SZB_ERR_NO_DEVICE;
+    }
+    SZB_REQUIRE(device >= 0 && device < n_dev, "szb_ctx_create: device %d out of range (%d devices)", device, n_dev);
+    SZB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only and has no fallback", device, prop.major,
+                  prop.minor);
+        return SZB_ERR_NO_DEVICE;
+    }
+    szb_ctx* ctx = new szb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+        ctx->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            set_error("cudaStreamCreate failed");
+            return SZB_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev_start);
+    cudaEventCreate(&ctx->ev_stop);
+    szb_status s = upload_frontend_tables();
+    if (s != SZB_OK) {
+        szb_ctx_destroy(ctx);
+        return s;
+    }
+    *out = ctx;
+    return SZB_OK;
+}
+
+void szb_ctx_destroy(szb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    szb_comm_destroy(ctx);
+    for (auto& pr : ctx->ktime_pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
+                       &ctx->x })
+        b->release();
+    ctx->h_segs.release();
+    ctx->h_misc.release();
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+szb_status szb_ctx_sync(szb_ctx* ctx) {
+    SZB_REQUIRE(ctx, "szb_ctx_sync: ctx is NULL");
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+int32_t szb_ctx_sm_count(const szb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t szb_ctx_launch_count(const szb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+szb_status szb_timer_start(szb_ctx* ctx) {
+    SZB_REQUIRE(ctx, "szb_timer_start: ctx is NULL");
+    SZB_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return SZB_OK;
+}
+szb_status szb_timer_stop(szb_ctx* ctx, float* elapsed_ms) {
+    SZB_REQUIRE(ctx && elapsed_ms, "szb_timer_stop: NULL argument");
+    SZB_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    SZB_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    SZB_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev_start, ctx->ev_stop));
+    return SZB_OK;
+}
+szb_status szb_kernel_timing(szb_ctx* ctx, int32_t enable) {
+    SZB_REQUIRE(ctx, "szb_kernel_timing: ctx is NULL");
+    ctx->ktime_on = enable != 0;
+    return SZB_OK;
+}
+szb_status szb_kernel_timing_read(szb_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset) {
+    SZB_REQUIRE(ctx, "szb_kernel_timing_read: ctx is NULL");
+    SZB_TRY(drain_ktime(ctx));
+    if (total_ms) *total_ms = ctx->ktime_ms;
+    if (launches) *launches = ctx->ktime_launches;
+    if (reset) {
+        ctx->ktime_ms = 0.0;
+        ctx->ktime_launches = 0;
+    }
+    return SZB_OK;
+}
+
+szb_status szb_dev_alloc(szb_ctx* ctx, size_t bytes, void** dptr) {
+    SZB_REQUIRE(ctx && dptr, "szb_dev_alloc: NULL argument");
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return SZB_ERR_ALLOC;
+    }
+    return SZB_OK;
+}
+szb_status szb_dev_free(szb_ctx* ctx, void* dptr) {
+    SZB_REQUIRE(ctx, "szb_dev_free: ctx is NULL");
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SZB_CUDA(cudaFree(dptr));
+    return SZB_OK;
+}
+szb_status szb_memcpy_h2d(szb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    SZB_REQUIRE(ctx, "szb_memcpy_h2d: ctx is NULL");
+    SZB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+szb_status szb_memcpy_d2h(szb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    SZB_REQUIRE(ctx, "szb_memcpy_d2h: ctx is NULL");
+    SZB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+szb_status szb_host_alloc_pinned(size_t bytes, void** hptr) {
+    SZB_REQUIRE(hptr, "szb_host_alloc_pinned: NULL argument");
+    cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return SZB_ERR_ALLOC;
+    }
+    return SZB_OK;
+}
+szb_status szb_host_free_pinned(void* hptr) {
+    SZB_CUDA(cudaFreeHost(hptr));
+    return SZB_OK;
+}
+
+// ---- tables ---------------------------------------------------------------------------------------------------------
+szb_status szb_table_mel(float* out) {
+    SZB_REQUIRE(out, "szb_table_mel: out is NULL");
+    const auto d = mel_filterbank_dense();
+    std::memcpy(out, d.data(), d.size() * sizeof(float));
+    return SZB_OK;
+}
+szb_status szb_table_dct(float* out) {
+    SZB_REQUIRE(out, "szb_table_dct: out is NULL");
+    const auto d = dct2_rows();
+    std::memcpy(out, d.data(), d.size() * sizeof(float));
+    return SZB_OK;
+}
+szb_status szb_table_resample_taps(uint32_t rate, float* out, uint32_t* L, uint32_t* M) {
+    SZB_REQUIRE(rate > 0, "szb_table_resample_taps: rate is 0");
+    uint32_t l, m;
+    resample_ratio(rate, l, m);
+    if (L) *L = l;
+    if (M) *M = m;
+    if (out) {
+        const auto c = resample_taps(rate);
+        std::memcpy(out, c.data(), c.size() * sizeof(float));
+    }
+    return SZB_OK;
+}
+
+// ---- front end ------------------------------------------------------------------------------------------------------
+uint64_t szb_num_windows(uint64_t n) { return n < SZB_WINDOW_SIZE ? 0 : (n - SZB_WINDOW_SIZE) / SZB_HOP_SIZE + 1; }
+uint64_t szb_resample_out_len(uint64_t n_in, uint32_t rate) {
+    if (rate == 0) return 0;
+    return uint64_t((unsigned __int128)n_in * SZB_SAMPLE_RATE / rate);
+}
+
+uint64_t szb_extract_batch_windows(const uint64_t* clip_off, uint32_t n_clips, uint32_t rate) {
+    if (!clip_off || rate == 0) return 0;
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_clips; ++c) {
+        const uint64_t n_in = clip_off[c + 1] - clip_off[c];
+        total += szb_num_windows(rate == SZB_SAMPLE_RATE ? n_in : szb_resample_out_len(n_in, rate));
+    }
+    return total;
+}
+
+szb_status szb_downmix_to_mono(szb_ctx* ctx, const int16_t* in, uint64_t n, uint32_t channels, int16_t* mono,
+                               uint64_t mono_cap, uint64_t* n_mono) {
+    SZB_REQUIRE(ctx && n_mono && (in || n == 0), "szb_downmix_to_mono: NULL argument");
+    const uint64_t ch = channels <= 1 ? 1 : channels;
+    const uint64_t n_out = (n + ch - 1) / ch;
+    *n_mono = n_out;
+    SZB_REQUIRE(mono_cap >= n_out && (mono || n_out == 0), "szb_downmix_to_mono: capacity %llu < %llu",
+                (unsigned long long)mono_cap, (unsigned long long)n_out);
+    if (n_out == 0) return SZB_OK;
+    if (ch == 1) {  // lib.rs:173-175
+        std::memcpy(mono, in, n * sizeof(int16_t));
+        return SZB_OK;
+    }
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->pcm.reserve(n * 2));
+    SZB_TRY(ctx->misc.reserve(n_out * 2));
+    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, in, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(launch_downmix(ctx, ctx->pcm.as<int16_t>(), n, uint32_t(ch), ctx->misc.as<int16_t>(), n_out));
+    SZB_CUDA(cudaMemcpyAsync(mono, ctx->misc.ptr, n_out * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in, uint32_t rate, int16_t* out,
+                                 uint64_t out_cap, uint64_t* n_out) {
+    SZB_REQUIRE(ctx && n_out && (in || n_in == 0), "szb_resample_to_44100: NULL argument");
+    SZB_REQUIRE(rate > 0, "szb_resample_to_44100: rate is 0");
+    const uint64_t n = rate == SZB_SAMPLE_RATE ? n_in : szb_resample_out_len(n_in, rate);
+    *n_out = n;
+    SZB_REQUIRE(out_cap >= n && (out || n == 0), "szb_resample_to_44100: capacity %llu < %llu",
+                (unsigned long long)out_cap, (unsigned long long)n);
+    if (n == 0) return SZB_OK;
+    if (rate == SZB_SAMPLE_RATE) {  // lib.rs:187-189
+        std::memcpy(out, in, n * sizeof(int16_t));
+        return SZB_OK;
+    }
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->pcm.reserve(n_in * 2));
+    SZB_TRY(ctx->misc.reserve(n * 2 + 64));
+    SZB_TRY(ctx->labels.reserve(4 * sizeof(uint64_t)));
+    const uint64_t offs[4] = { 0, n_in, 0, n };
+    SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, in, n_in * 2, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(launch_resample(ctx, ctx->pcm.as<int16_t>(), ctx->labels.as<uint64_t>(), ctx->labels.as<uint64_t>() + 2, 1, n,
+                            rate, ctx->misc.as<int16_t>()));
+    SZB_CUDA(cudaMemcpyAsync(out, ctx->misc.ptr, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_extract_batch_dev(szb_ctx* ctx, const int16_t* d_pcm, const uint64_t* clip_off, uint32_t n_clips,
+                                 uint32_t rate, float* d_feats, uint64_t cap_windows, uint64_t* win_off) {
+    SZB_REQUIRE(ctx && clip_off && win_off, "szb_extract_batch_dev: NULL argument");
+    SZB_REQUIRE(rate > 0, "szb_extract_batch_dev: rate is 0");
+    for (uint32_t c = 0; c < n_clips; ++c)
+        SZB_REQUIRE(clip_off[c + 1] >= clip_off[c], "szb_extract_batch_dev: clip_off not monotone at %u", c);
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> off44, woff;
+    batch_layout(clip_off, n_clips, rate, off44, woff);
+    std::memcpy(win_off, woff.data(), woff.size() * sizeof(uint64_t));
+    const uint64_t total = woff[n_clips];
+    SZB_REQUIRE(cap_windows >= total, "szb_extract_batch_dev: capacity %llu windows < %llu", (unsigned long long)cap_windows,
+                (unsigned long long)total);
+    if (total == 0) return SZB_OK;
+    SZB_REQUIRE(d_pcm && d_feats, "szb_extract_batch_dev: NULL device pointer");
+    const int16_t* d_pcm44 = d_pcm + clip_off[0];
+    if (rate != SZB_SAMPLE_RATE) {
+        // unfused path: resample every clip into a 44.1 kHz scratch buffer, then extract from it
+        SZB_TRY(ctx->misc.reserve(off44[n_clips] * 2 + 64));
+        SZB_TRY(ctx->labels.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
+        SZB_TRY(ctx->h_misc.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
+        uint64_t* h = ctx->h_misc.as<uint64_t>();
+        std::memcpy(h, clip_off, (size_t(n_clips) + 1) * sizeof(uint64_t));
+        uint64_t* h_out = h + n_clips + 1;
+        uint64_t max_out = 0;
+        for (uint32_t c = 0; c <= n_clips; ++c) h_out[c] = off44[c];
+        for (uint32_t c = 0; c < n_clips; ++c)
+            max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
+        SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, h, (size_t(n_clips) + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        SZB_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, off44[n_clips] * 2 + 64, ctx->stream));
+        SZB_TRY(launch_resample(ctx, d_pcm, ctx->labels.as<uint64_t>(), ctx->labels.as<uint64_t>() + n_clips + 1, n_clips,
+                                max_out, rate, ctx->misc.as<int16_t>()));
+        d_pcm44 = ctx->misc.as<int16_t>();
+    }
+    std::vector<Segment> segs;
+    build_segments(off44.data(), woff.data(), n_clips, ctx->sm_count, segs);
+    return launch_extract(ctx, d_pcm44, segs, d_feats);
+}
+
+szb_status szb_extract_batch(szb_ctx* ctx, const int16_t* pcm, const uint64_t* clip_off, uint32_t n_clips, uint32_t rate,
+                             float* feats, uint64_t cap_windows, uint64_t* win_off) {
+    SZB_REQUIRE(ctx && clip_off && win_off, "szb_extract_batch: NULL argument");
+    SZB_REQUIRE(rate > 0, "szb_extract_batch: rate is 0");
+    const uint64_t total = szb_extract_batch_windows(clip_off, n_clips, rate);
+    SZB_REQUIRE(cap_windows >= total, "szb_extract_batch: capacity %llu windows < %llu", (unsigned long long)cap_windows,
+                (unsigned long long)total);
+    const uint64_t first = n_clips ? clip_off[0] : 0, last = n_clips ? clip_off[n_clips] : 0;
+    const uint64_t n_samples = last - first;
+    if (total == 0 || n_samples == 0) {
+        win_off[0] = 0;
+        for (uint32_t c = 0; c < n_clips; ++c) win_off[c + 1] = 0;
+        return SZB_OK;
+    }
+    SZB_REQUIRE(pcm && feats, "szb_extract_batch: NULL buffer");
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->pcm.reserve(n_samples * 2 + 64));
+    SZB_TRY(ctx->feats.reserve(total * SZB_FEATURE_SIZE * sizeof(float)));
+    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, pcm + first, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint64_t> rel(size_t(n_clips) + 1);
+    for (uint32_t c = 0; c <= n_clips; ++c) rel[c] = clip_off[c] - first;
+    SZB_TRY(szb_extract_batch_dev(ctx, ctx->pcm.as<int16_t>(), rel.data(), n_clips, rate, ctx->feats.as<float>(), total,
+                                  win_off));
+    SZB_CUDA(cudaMemcpyAsync(feats, ctx->feats.ptr, total * SZB_FEATURE_SIZE * sizeof(float), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_extract(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, float* feats, uint64_t cap_windows,
+                       uint64_t* n_windows) {
+    SZB_REQUIRE(ctx && n_windows, "szb_extract: NULL argument");
+    const uint64_t off[2] = { 0, n_samples };
+    uint64_t woff[2] = { 0, 0 };
+    *n_windows = szb_num_windows(n_samples);
+    SZB_TRY(szb_extract_batch(ctx, pcm, off, 1, SZB_SAMPLE_RATE, feats, cap_windows, woff));
+    return SZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Multi-GPU plumbing: one process per GPU; batch-parallel training all-reduces the flattened gradient (+ the
+// [n_used, loss] tail) once per step with NCCL over NVLink/NVSwitch -- the only collective of the path
+// (BASELINE.json north_star).  Extraction shards clips across ranks and needs no collective.
+//
+// NCCL is bound at run time with dlopen so the library has no link-time NCCL dependency: a host that never calls
+// szb_comm_* (single GPU, or the Rust CLI) does not need libnccl at all, and inside a PyTorch process the already
+// loaded libnccl.so.2 is reused instead of a second copy.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace szb {
+
+struct Id128 { char bytes[128]; };  // ncclUniqueId, passed by value
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static szb_status load_nccl() {
+    if (g_nccl.handle) return SZB_OK;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        return SZB_ERR_NCCL;
+    }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        set_error("libnccl is missing a required symbol");
+        dlclose(h);
+        return SZB_ERR_NCCL;
+    }
+    g_nccl.handle = h;
+    return SZB_OK;
+}
+
+#define SZB_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        int _r = (expr);                                                                                 \
+        if (_r != 0) {                                                                                   \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");  \
+            return SZB_ERR_NCCL;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n) {
+    if (ctx->world <= 1) return SZB_OK;
+    SZB_REQUIRE(ctx->nccl_comm, "all-reduce requested but szb_comm_init was not called");
+    // ncclFloat32 = 7, ncclSum = 0
+    SZB_NCCL(g_nccl.AllReduce(buf, buf, n, 7, 0, ctx->nccl_comm, ctx->stream));
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+}  // namespace szb
+
+using namespace szb;
+
+extern "C" {
+
+szb_status szb_comm_unique_id(uint8_t id[128]) {
+    SZB_REQUIRE(id, "szb_comm_unique_id: id is NULL");
+    SZB_TRY(load_nccl());
+    SZB_NCCL(g_nccl.GetUniqueId(id));
+    return SZB_OK;
+}
+
+szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world) {
+    SZB_REQUIRE(ctx && id, "szb_comm_init: NULL argument");
+    SZB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "szb_comm_init: bad rank %d / world %d", rank, world);
+    SZB_REQUIRE(!ctx->nccl_comm, "szb_comm_init: communicator already initialised");
+    ctx->rank = rank;
+    ctx->world = world;
+    if (world == 1) return SZB_OK;
+    SZB_TRY(load_nccl());
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    Id128 uid;
+    std::memcpy(uid.bytes, id, 128);
+    SZB_NCCL(g_nccl.CommInitRank(&ctx->nccl_comm, world, uid, rank));
+    return SZB_OK;
+}
+
+szb_status szb_comm_destroy(szb_ctx* ctx) {
+    if (!ctx) return SZB_OK;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaSetDevice(ctx->device);
+        g_nccl.CommDestroy(ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return SZB_OK;
+}
+
+int32_t szb_comm_world(const szb_ctx* ctx) { return ctx ? ctx->world : 1; }
+
+}  // extern "C"

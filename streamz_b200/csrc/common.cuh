@@ -1,0 +1,79 @@
+// Shared internals of libstreamz_b200: context, error plumbing, growable device scratch.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/streamz_b200.h"
+
+namespace szb {
+
+void set_error(const char* fmt, ...);
+
+#define SZB_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::szb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return SZB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define SZB_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::szb::set_error(__VA_ARGS__); \
+            return SZB_ERR_INVALID;       \
+        }                                 \
+    } while (0)
+
+#define SZB_TRY(expr)                     \
+    do {                                  \
+        szb_status _s = (expr);           \
+        if (_s != SZB_OK) return _s;      \
+    } while (0)
+
+// A device buffer that only grows; reused across calls so steady-state calls do no cudaMalloc.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    szb_status reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct PinnedBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    szb_status reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+}  // namespace szb
+
+struct szb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // chunk pipeline of the host entry points
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
+    uint64_t launches = 0;
+    // per-launch timing of the extraction kernel (roofline figure)
+    bool ktime_on = false;
+    double ktime_ms = 0.0;
+    uint64_t ktime_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime_pending;
+    // scratch
+    szb::DevBuf segs, counter, pcm, feats, taps, labels, misc, probs, x;
+    szb::PinnedBuf h_segs, h_misc;
+    uint32_t taps_rate = 0;  // rate the taps buffer currently holds
+    // NCCL (loaded lazily with dlopen; see comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};

@@ -1,0 +1,402 @@
+// Front end of the StreamZ hot path as one fused sm_100a kernel:
+//   i16 PCM @ 44.1 kHz -> 800-sample frames, hop 400 -> FFT -> |X|^2 (bins 0..400) -> 26 mel bands -> ln
+//   -> DCT-II (20 coeffs) -> delta, delta-delta -> per-window z-score -> [n][60] f32
+// Reference: FeatureExtractor::extract -> window_samples_with_plan, streamz-rs/src/lib.rs:261-345
+// (no pre-emphasis, rectangular window, unnormalised FFT: lib.rs:292-301).
+//
+// Mapping (see DESIGN.md "Front-end kernel"): one persistent CTA per SM pulls (clip, window-range) segments from an
+// atomic queue and walks each segment in tiles of 32 frames.  LANE = FRAME everywhere: the 32 lanes of a warp hold
+// the same element of 32 consecutive frames, so every shared-memory row is [.. ][32 lanes] and every access is
+// conflict-free by construction, every twiddle / mel / DCT coefficient is warp-uniform (constant bank), and each
+// thread runs whole 20-point DFTs in registers.  Each PCM sample is read from HBM once per tile (+1 hop of overlap
+// between tiles), each feature row is written once with 16-byte coalesced stores; MFCCs of the previous tile stay in
+// a shared-memory ring so the +-2-frame delta stencil never recomputes or re-reads anything inside a segment.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "fft_math.cuh"
+#include "frontend.cuh"
+#include "tables.hpp"
+
+namespace szb {
+
+// ---- constant tables (uploaded per device at context creation) ------------------------------------------------------
+__constant__ float2 c_tw400[kR * kR];     // W_400^{n1 k2}
+__constant__ float2 c_tw800[201];         // W_800^k, k = 0..200
+__constant__ float c_melw[768];           // non-zero mel weights, pre-scaled by 1 / (4 * 32767^2)
+__constant__ int c_mel_start[kMels];
+__constant__ int c_mel_len[kMels];
+__constant__ int c_mel_off[kMels];
+__constant__ float c_dct[kMfcc * kMels];  // unscaled DCT-II rows
+
+constexpr int kTile = 32;                 // frames per tile == lanes per warp
+constexpr int kWarps = 20;                // one warp per 20-point DFT column
+constexpr int kThreads = kWarps * 32;
+constexpr int kHopWords = kHop / 2;       // 200 packed (i16,i16) words per hop
+constexpr int kHopStride = kHopWords + 1; // 201: odd lane stride -> conflict-free 32-bit reads with lane = frame
+constexpr int kPcmRows = kTile + 1;       // 33 hops cover 32 frames
+constexpr int kRing = 64;                 // MFCC ring slots (power of two >= kTile + 4)
+
+constexpr size_t kSmemPcm = size_t(kPcmRows) * kHopStride * 4;          // 26 532
+constexpr size_t kSmemS = size_t(kHalf) * kTile * 8;                    // 102 400
+constexpr size_t kSmemP = size_t(kBins) * kTile * 4;                    // 51 328
+constexpr size_t kSmemE = size_t(kMels) * kTile * 4;                    // 3 328
+constexpr size_t kSmemRing = size_t(kMfcc) * kRing * 4;                 // 5 120
+constexpr size_t kSmemRed = size_t(kWarps) * 32 * 4;                    // 2 560
+constexpr size_t kSmemOut = size_t(kTile) * kFeat * 4;                  // 7 680
+constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+constexpr size_t kOffPcm = 0;
+constexpr size_t kOffS = align16(kOffPcm + kSmemPcm);
+constexpr size_t kOffP = align16(kOffS + kSmemS);
+constexpr size_t kOffE = align16(kOffP + kSmemP);
+constexpr size_t kOffRing = align16(kOffE + kSmemE);
+constexpr size_t kOffRed = align16(kOffRing + kSmemRing);
+constexpr size_t kOffOut = align16(kOffRed + kSmemRed);
+constexpr size_t kSmemTotal = align16(kOffOut + kSmemOut);
+static_assert(kSmemTotal <= 227 * 1024, "front-end tile does not fit in shared memory");
+
+__device__ __forceinline__ float s16lo(uint32_t v) { return float(int(short(v & 0xffffu))); }
+__device__ __forceinline__ float s16hi(uint32_t v) { return float(int(v) >> 16); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs, uint32_t n_segs,
+               unsigned int* __restrict__ queue, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* s_pcm = reinterpret_cast<uint32_t*>(smem + kOffPcm);
+    float2* s_S = reinterpret_cast<float2*>(smem + kOffS);
+    float* s_P = reinterpret_cast<float*>(smem + kOffP);
+    float* s_E = reinterpret_cast<float*>(smem + kOffE);
+    float* s_ring = reinterpret_cast<float*>(smem + kOffRing);
+    float* s_red = reinterpret_cast<float*>(smem + kOffRed);
+    float* s_out = reinterpret_cast<float*>(smem + kOffOut);
+    __shared__ uint32_t s_seg;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (;;) {
+        if (tid == 0) s_seg = atomicAdd(queue, 1u);
+        __syncthreads();
+        const uint32_t si = s_seg;
+        __syncthreads();
+        if (si >= n_segs) break;
+        const Segment sg = segs[si];
+        const uint32_t n_total = sg.n_total;
+        const uint32_t f_lo = sg.w_begin >= 2 ? sg.w_begin - 2 : 0;
+        const uint32_t f_hi = min(sg.w_end + 2, n_total);
+        const int16_t* clip = pcm + sg.pcm_off;
+        const bool aligned32 = (reinterpret_cast<uintptr_t>(clip) & 3) == 0;
+        float* out_clip = out + sg.out_row * kFeat;
+        uint32_t emit_next = sg.w_begin;
+
+        for (uint32_t a = f_lo; a < f_hi; a += kTile) {
+            const uint32_t nf = min(uint32_t(kTile), f_hi - a);
+            // ---- 1. stage hops [a, a + nf] as packed i16 pairs; rows past the tile are zero-filled -------------------
+            {
+                const int16_t* src = clip + size_t(a) * kHop;
+                const uint32_t nh = nf + 1;
+                for (int i = tid; i < kPcmRows * kHopWords; i += kThreads) {
+                    const int h = i / kHopWords, wd = i - h * kHopWords;
+                    uint32_t v = 0;
+                    if (uint32_t(h) < nh) {
+                        const size_t s = size_t(h) * kHop + size_t(wd) * 2;
+                        if (aligned32) {
+                            v = __ldg(reinterpret_cast<const uint32_t*>(src + s));
+                        } else {
+                            const uint32_t lo = uint16_t(__ldg(src + s)), hi = uint16_t(__ldg(src + s + 1));
+                            v = lo | (hi << 16);
+                        }
+                    }
+                    s_pcm[h * kHopStride + wd] = v;
+                }
+            }
+            __syncthreads();
+
+            // ---- 2. stage A: warp = n1, lane = frame.  20-point DFT over n2 of z[n1 + 20 n2], twiddle, transpose ----
+            {
+                const int n1 = warp;
+                const uint32_t* pw = s_pcm + lane * kHopStride + n1;
+                float re[kR], im[kR];
+#pragma unroll
+                for (int n2 = 0; n2 < kR; ++n2) {
+                    // z[n] lives in hop `lane` for n < 200 and in hop `lane + 1` (row stride 201 = 200 + 1) above
+                    const uint32_t v = pw[kR * n2 + (n2 >= kR / 2 ? 1 : 0)];
+                    re[n2] = s16lo(v);
+                    im[n2] = s16hi(v);
+                }
+                dft20(re, im);
+                float2* dst = s_S + n1 * kTile + lane;
+                dst[0] = make_float2(re[0], im[0]);
+#pragma unroll
+                for (int k2 = 1; k2 < kR; ++k2) {
+                    const float2 w = c_tw400[n1 * kR + k2];
+                    dst[k2 * kR * kTile] = make_float2(fmaf(re[k2], w.x, -(im[k2] * w.y)), fmaf(re[k2], w.y, im[k2] * w.x));
+                }
+            }
+            __syncthreads();
+
+            // ---- 3. stage B: warp = k2, lane = frame.  20-point DFT over n1, in place: row k2*20 + k1 = Z[k2 + 20 k1] --
+            {
+                float2* col = s_S + warp * kR * kTile + lane;
+                float re[kR], im[kR];
+#pragma unroll
+                for (int n1 = 0; n1 < kR; ++n1) {
+                    const float2 v = col[n1 * kTile];
+                    re[n1] = v.x;
+                    im[n1] = v.y;
+                }
+                dft20(re, im);
+#pragma unroll
+                for (int k1 = 0; k1 < kR; ++k1) col[k1 * kTile] = make_float2(re[k1], im[k1]);
+            }
+            __syncthreads();
+
+            // ---- 4. real-input split + power: warp-uniform k, lane = frame -------------------------------------------
+            for (int k = warp; k <= 200; k += kWarps) {
+                if (k == 0) {
+                    const float2 z = s_S[lane];
+                    const float p0 = z.x + z.y, p1 = z.x - z.y;
+                    s_P[lane] = 4.f * p0 * p0;
+                    s_P[400 * kTile + lane] = 4.f * p1 * p1;
+                } else {
+                    const float2 za = s_S[row_of_bin(k) * kTile + lane];
+                    const float2 zb = s_S[row_of_bin(kHalf - k) * kTile + lane];
+                    const float2 w = c_tw800[k];
+                    float pk, pmk;
+                    split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
+                    s_P[k * kTile + lane] = pk;
+                    s_P[(kHalf - k) * kTile + lane] = pmk;
+                }
+            }
+            __syncthreads();
+
+            // ---- 5. mel + ln: warp-uniform filter, lane = frame (sparse rows of the 26 x 401 bank, lib.rs:303-310) -----
+            for (int m = warp; m < kMels; m += kWarps) {
+                const int k0 = c_mel_start[m], len = c_mel_len[m];
+                const float* wv = c_melw + c_mel_off[m];
+                const float* pp = s_P + k0 * kTile + lane;
+                float acc = 0.f;
+                for (int i = 0; i < len; ++i) acc = fmaf(wv[i], pp[i * kTile], acc);
+                s_E[m * kTile + lane] = logf(fmaxf(acc, 1e-12f));
+            }
+            __syncthreads();
+
+            // ---- 6. DCT-II, first 20 coefficients: warp = coefficient, lane = frame (lib.rs:312-315) -------------------
+            {
+                const int j = warp;
+                float acc = 0.f;
+#pragma unroll
+                for (int m = 0; m < kMels; ++m) acc = fmaf(c_dct[j * kMels + m], s_E[m * kTile + lane], acc);
+                if (uint32_t(lane) < nf) s_ring[j * kRing + ((a + lane) & (kRing - 1))] = acc;
+            }
+            __syncthreads();
+
+            // ---- 7. delta, delta-delta, z-score and store for the windows whose +-2 neighbours are now known ----------
+            const bool last = a + nf >= f_hi;
+            const uint32_t lim = last ? sg.w_end : min(sg.w_end, a + nf - 2);
+            for (uint32_t w0 = emit_next; w0 < lim; w0 += kTile) {
+                const uint32_t w = w0 + lane;
+                const bool valid = w < lim;
+                const int j = warp;
+                float c0 = 0.f, d1 = 0.f, d2 = 0.f;
+                if (valid) {
+                    const int hi = int(n_total) - 1;
+                    const float* rj = s_ring + j * kRing;
+                    auto cl = [hi](int x) { return min(max(x, 0), hi); };
+                    auto C = [rj](int g) { return rj[g & (kRing - 1)]; };
+                    const int ip = cl(int(w) + 1), im = cl(int(w) - 1);
+                    c0 = C(int(w));
+                    d1 = (C(ip) - C(im)) * 0.5f;                                   // lib.rs:223
+                    const float dp = (C(cl(ip + 1)) - C(cl(ip - 1))) * 0.5f;       // delta at clamp(w+1)
+                    const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;       // delta at clamp(w-1)
+                    d2 = (dp - dm) * 0.5f;                                         // lib.rs:322
+                }
+                s_red[warp * 32 + lane] = c0 + d1 + d2;
+                __syncthreads();
+                float sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < kWarps; ++q) sum += s_red[q * 32 + lane];
+                const float mean = sum / float(kFeat);                             // lib.rs:328
+                __syncthreads();
+                const float e0 = c0 - mean, e1 = d1 - mean, e2 = d2 - mean;
+                s_red[warp * 32 + lane] = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+                __syncthreads();
+                float var = 0.f;
+#pragma unroll
+                for (int q = 0; q < kWarps; ++q) var += s_red[q * 32 + lane];
+                var = var / float(kFeat);                                          // lib.rs:329-336
+                const float sd = fmaxf(sqrtf(var), 1e-6f);                         // lib.rs:337
+                s_out[lane * kFeat + j] = e0 / sd;                                 // lib.rs:338-340
+                s_out[lane * kFeat + kMfcc + j] = e1 / sd;
+                s_out[lane * kFeat + 2 * kMfcc + j] = e2 / sd;
+                __syncthreads();
+                const uint32_t nvalid = min(uint32_t(kTile), lim - w0);
+                float4* dst = reinterpret_cast<float4*>(out_clip + size_t(w0) * kFeat);
+                const float4* srcv = reinterpret_cast<const float4*>(s_out);
+                for (uint32_t i = tid; i < nvalid * (kFeat / 4); i += kThreads) dst[i] = srcv[i];
+                __syncthreads();
+            }
+            emit_next = max(emit_next, lim);
+        }
+    }
+}
+
+// ---- standalone resampler (resample_to_44100, lib.rs:186-209; polyphase spec in DESIGN.md) ---------------------------
+// One thread per output sample; taps [L][16] in global memory (L1/L2 resident).  Bit-exact contract:
+// acc = fma(c[p][t], float(x[i]), acc), t = 0..15, then clamp and truncate toward zero.
+__global__ void resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_off,
+                                const uint64_t* __restrict__ out_off, uint32_t n_clips, const float* __restrict__ taps,
+                                uint32_t L, uint32_t M, uint32_t rate, int16_t* __restrict__ out) {
+    const uint32_t c = blockIdx.y;
+    if (c >= n_clips) return;
+    const uint64_t n_in = in_off[c + 1] - in_off[c];
+    const uint64_t n_out = n_in * 44100ull / rate;  // lib.rs:196 (out_off may be padded past this)
+    const int16_t* x = in + in_off[c];
+    int16_t* y = out + out_off[c];
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n_out; j += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t pos = j * M;
+        const int64_t i0 = int64_t(pos / L);
+        const uint32_t p = uint32_t(pos - uint64_t(i0) * L);
+        const float4* cp = reinterpret_cast<const float4*>(taps + size_t(p) * kResTaps);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < kResTaps / 4; ++q) {
+            const float4 cv = __ldg(cp + q);
+            const float cs[4] = { cv.x, cv.y, cv.z, cv.w };
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t i = i0 - (kResTaps / 2 - 1) + q * 4 + r;
+                const float xv = (i >= 0 && uint64_t(i) < n_in) ? float(x[i]) : 0.f;
+                acc = fmaf(cs[r], xv, acc);
+            }
+        }
+        acc = fminf(fmaxf(acc, -32768.f), 32767.f);
+        y[j] = int16_t(__float2int_rz(acc));
+    }
+}
+
+// downmix_to_mono (lib.rs:172-183)
+__global__ void downmix_kernel(const int16_t* __restrict__ in, uint64_t n_in, uint32_t ch, int16_t* __restrict__ out,
+                               uint64_t n_out) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_out; i += uint64_t(gridDim.x) * blockDim.x) {
+        int32_t sum = 0;
+        for (uint32_t c = 0; c < ch; ++c) {
+            const uint64_t s = i * ch + c;
+            if (s < n_in) sum += int32_t(in[s]);
+        }
+        out[i] = int16_t(sum / int32_t(ch));  // C++ integer division truncates toward zero like Rust
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+
+szb_status upload_frontend_tables() {
+    const auto tw400 = twiddles_400();
+    const auto tw800 = twiddles_800_half();
+    const auto dense = mel_filterbank_dense();
+    const MelCsr csr = mel_filterbank_csr(dense);
+    const auto dct = dct2_rows();
+    SZB_REQUIRE(csr.w.size() <= 768, "mel bank has %zu non-zeros, table holds 768", csr.w.size());
+    std::vector<float> melw(768, 0.f);
+    const double scale = 1.0 / (4.0 * 32767.0 * 32767.0);  // undo integer-valued input and the unscaled real split
+    for (size_t i = 0; i < csr.w.size(); ++i) melw[i] = float(double(csr.w[i]) * scale);
+    SZB_CUDA(cudaMemcpyToSymbol(c_tw400, tw400.data(), tw400.size() * sizeof(float)));
+    SZB_CUDA(cudaMemcpyToSymbol(c_tw800, tw800.data(), tw800.size() * sizeof(float)));
+    SZB_CUDA(cudaMemcpyToSymbol(c_melw, melw.data(), melw.size() * sizeof(float)));
+    SZB_CUDA(cudaMemcpyToSymbol(c_mel_start, csr.start, sizeof(csr.start)));
+    SZB_CUDA(cudaMemcpyToSymbol(c_mel_len, csr.len, sizeof(csr.len)));
+    SZB_CUDA(cudaMemcpyToSymbol(c_mel_off, csr.off, sizeof(int) * kMels));
+    SZB_CUDA(cudaMemcpyToSymbol(c_dct, dct.data(), dct.size() * sizeof(float)));
+    SZB_CUDA(cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
+    return SZB_OK;
+}
+
+// Split clips into (clip, window-range) segments: whole clips when there is enough work to fill the machine, else
+// ranges of >= 64 windows so short batches still spread over the SMs.
+void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_t n_clips, int sm_count,
+                    std::vector<Segment>& segs) {
+    segs.clear();
+    const uint64_t total = win_off[n_clips];
+    uint64_t target = total / (uint64_t(sm_count) * 4);
+    target = std::max<uint64_t>(64, std::min<uint64_t>(target, 4096));
+    target = (target + kTile - 1) / kTile * kTile;
+    for (uint32_t c = 0; c < n_clips; ++c) {
+        const uint64_t n = win_off[c + 1] - win_off[c];
+        if (n == 0) continue;
+        const uint64_t parts = (n + target + target / 2 - 1) / (target + target / 2);  // allow 1.5x target per segment
+        const uint64_t np = std::max<uint64_t>(1, parts);
+        for (uint64_t p = 0; p < np; ++p) {
+            Segment s;
+            s.pcm_off = clip_off44[c];
+            s.out_row = win_off[c];
+            s.n_total = uint32_t(n);
+            s.w_begin = uint32_t(n * p / np);
+            s.w_end = uint32_t(n * (p + 1) / np);
+            if (s.w_end > s.w_begin) segs.push_back(s);
+        }
+    }
+}
+
+szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, const std::vector<Segment>& segs, float* d_feats) {
+    if (segs.empty()) return SZB_OK;
+    SZB_TRY(ctx->segs.reserve(segs.size() * sizeof(Segment)));
+    SZB_TRY(ctx->counter.reserve(sizeof(unsigned int)));
+    SZB_TRY(ctx->h_segs.reserve(segs.size() * sizeof(Segment)));
+    std::memcpy(ctx->h_segs.ptr, segs.data(), segs.size() * sizeof(Segment));
+    SZB_CUDA(cudaMemcpyAsync(ctx->segs.ptr, ctx->h_segs.ptr, segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    SZB_CUDA(cudaMemsetAsync(ctx->counter.ptr, 0, sizeof(unsigned int), ctx->stream));
+    const int grid = int(std::min<size_t>(segs.size(), size_t(ctx->sm_count)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->ktime_on) {
+        SZB_CUDA(cudaEventCreate(&e0));
+        SZB_CUDA(cudaEventCreate(&e1));
+        SZB_CUDA(cudaEventRecord(e0, ctx->stream));
+    }
+    extract_kernel<<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>(), uint32_t(segs.size()),
+                                                               ctx->counter.as<unsigned int>(), d_feats);
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (ctx->ktime_on) {
+        SZB_CUDA(cudaEventRecord(e1, ctx->stream));
+        ctx->ktime_pending.emplace_back(e0, e1);
+    }
+    return SZB_OK;
+}
+
+szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
+                           uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
+    if (n_clips == 0 || max_out == 0) return SZB_OK;
+    uint32_t L, M;
+    resample_ratio(rate, L, M);
+    if (ctx->taps_rate != rate) {
+        const auto taps = resample_taps(rate);
+        SZB_TRY(ctx->taps.reserve(taps.size() * sizeof(float)));
+        SZB_CUDA(cudaMemcpyAsync(ctx->taps.ptr, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(cudaStreamSynchronize(ctx->stream));  // taps is a temporary
+        ctx->taps_rate = rate;
+    }
+    const int threads = 256;
+    const uint64_t bx = std::min<uint64_t>((max_out + threads - 1) / threads, 4096);
+    for (uint32_t c0 = 0; c0 < n_clips; c0 += 65535) {
+        const uint32_t nc = std::min<uint32_t>(65535, n_clips - c0);
+        dim3 grid(uint32_t(bx), nc);
+        resample_kernel<<<grid, threads, 0, ctx->stream>>>(d_in, d_in_off + c0, d_out_off + c0, nc, ctx->taps.as<float>(), L,
+                                                           M, rate, d_out);
+        SZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return SZB_OK;
+}
+
+szb_status launch_downmix(szb_ctx* ctx, const int16_t* d_in, uint64_t n_in, uint32_t ch, int16_t* d_out, uint64_t n_out) {
+    if (n_out == 0) return SZB_OK;
+    const int threads = 256;
+    const uint64_t blocks = std::min<uint64_t>((n_out + threads - 1) / threads, uint64_t(ctx->sm_count) * 16);
+    downmix_kernel<<<uint32_t(blocks), threads, 0, ctx->stream>>>(d_in, n_in, ch, d_out, n_out);
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+}  // namespace szb

@@ -1,0 +1,651 @@
+// SimpleNeuralNet (streamz-rs/src/lib.rs:745-1060) on the GPU: batched forward, cross-entropy backward, SGD, and the
+// per-window aggregation of identify_speaker_list (lib.rs:1383-1411).
+//
+// This file holds the FP32 path for arbitrary layer sizes (the reference's constructor is generic, lib.rs:767, and its
+// own test uses a 4-3-2-2 net, lib.rs:1834): a register-tiled SIMT GEMM with the layer epilogues fused
+// (bias+ReLU, bias+tanh, bias, *tanh', *ReLU').  Results follow the reference's arithmetic in FP32 exactly up to
+// summation order.  See DESIGN.md "MLP kernels".
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "mlp.cuh"
+
+namespace szb {
+
+// ---- counter RNG shared with the oracle (oracle/streamz_oracle.py: dropout_keep_mask) -------------------------------
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ unsigned long long dropout_key(unsigned long long seed, unsigned long long stream) {
+    return splitmix64(seed + stream * 0xD1B54A32D192ED03ull);
+}
+// true = keep.  u = 24 random bits * 2^-24 in [0,1); dropped when u < prob (rng.gen::<f32>() < prob, lib.rs:125)
+__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long key, unsigned long long row, uint32_t i, float prob) {
+    const unsigned long long u = splitmix64(key ^ (row * 64ull + i));
+    const float r = float(uint32_t(u >> 40)) * 5.9604644775390625e-08f;
+    return !(r < prob);
+}
+
+// ---- SIMT GEMM with fused epilogues ----------------------------------------------------------------------------------
+enum Epi : int { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_TANH = 2, EPI_MUL_DTANH = 3, EPI_MUL_DRELU = 4, EPI_ATOMIC = 5 };
+
+constexpr int GB = 64;   // block tile M and N
+constexpr int GK = 16;   // block tile K
+constexpr int GT = 256;  // threads, each computes 4 x 4
+
+// C[M,N] (+)= op(A)[M,K] * op(B)[K,N].  TA: A is stored [K][M] (lda = row stride); TB: B is stored [N][K].
+// blockIdx.z splits K (only with EPI_ATOMIC).
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(GT) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                 const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                 const float* __restrict__ bias, const float* __restrict__ aux, int ldaux,
+                                                 int k_chunk) {
+    __shared__ float sA[GK][GB + 4];
+    __shared__ float sB[GK][GB + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+    const int kb = blockIdx.z * k_chunk, ke = min(K, kb + k_chunk);
+    float acc[4][4] = {};
+    for (int k0 = kb; k0 < ke; k0 += GK) {
+        // load A tile -> sA[k][m]
+        for (int i = tid; i < GB * GK; i += GT) {
+            int m, k;
+            if (TA) { m = i % GB; k = i / GB; } else { k = i % GK; m = i / GK; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < ke) v = TA ? A[size_t(gk) * lda + gm] : A[size_t(gm) * lda + gk];
+            sA[k][m] = v;
+        }
+        for (int i = tid; i < GB * GK; i += GT) {
+            int n, k;
+            if (TB) { k = i % GK; n = i / GK; } else { n = i % GB; k = i / GB; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < ke) v = TB ? B[size_t(gn) * ldb + gk] : B[size_t(gk) * ldb + gn];
+            sB[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (EPI == EPI_BIAS) v += bias[gn];
+            if (EPI == EPI_BIAS_RELU) { v += bias[gn]; v = v > 0.f ? v : 0.f; }           // lib.rs:882
+            if (EPI == EPI_BIAS_TANH) v = tanhf(v + bias[gn]);                             // lib.rs:883
+            if (EPI == EPI_MUL_DTANH) { const float h = aux[size_t(gm) * ldaux + gn]; v *= (1.f - h * h); }  // lib.rs:1034
+            if (EPI == EPI_MUL_DRELU) v = aux[size_t(gm) * ldaux + gn] > 0.f ? v : 0.f;   // lib.rs:1040
+            if (EPI == EPI_ATOMIC) atomicAdd(&C[size_t(gm) * ldc + gn], v);
+            else C[size_t(gm) * ldc + gn] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB, int EPI>
+static szb_status gemm(szb_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       const float* bias, const float* aux, int ldaux) {
+    if (M <= 0 || N <= 0) return SZB_OK;
+    dim3 grid((N + GB - 1) / GB, (M + GB - 1) / GB, 1);
+    int k_chunk = K;
+    if (EPI == EPI_ATOMIC) {
+        const int tiles = grid.x * grid.y;
+        int split = std::max(1, std::min((ctx->sm_count * 2 + tiles - 1) / tiles, (K + 4 * GK - 1) / (4 * GK)));
+        k_chunk = ((K + split - 1) / split + GK - 1) / GK * GK;
+        grid.z = (K + k_chunk - 1) / k_chunk;
+    }
+    gemm_kernel<TA, TB, EPI><<<grid, GT, 0, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, k_chunk);
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+// ---- row-wise softmax with the consumers fused ----------------------------------------------------------------------
+// One warp per row.  mode bits: 1 = write probabilities, 2 = training (delta3 = p - t in place of z, loss, count),
+// 4 = identify histogram (argmax_last / threshold), 8 = accumulate per-class probability sums.
+__global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, int mode, float* __restrict__ probs,
+                               const uint32_t* __restrict__ labels, const float* __restrict__ target_vec,
+                               const uint8_t* __restrict__ valid, float* __restrict__ tail, float threshold,
+                               unsigned long long* __restrict__ hist, float* __restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* zr = z + size_t(row) * ldz;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, zr[c]);                     // lib.rs:887
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(zr[c] - mx);                   // lib.rs:888-889
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const bool ok = valid ? valid[row] != 0 : true;
+    const uint32_t label = labels ? labels[row] : 0xffffffffu;
+    float best = -1.f;
+    int best_c = -1;
+    for (int c = lane; c < C; c += 32) {
+        const float p = expf(zr[c] - mx) / sum;                                   // lib.rs:890
+        if (mode & 1) probs[size_t(row) * C + c] = p;
+        if (mode & 2) {
+            const float t = target_vec ? target_vec[c] : (uint32_t(c) == label ? 1.f : 0.f);
+            zr[c] = ok ? p - t : 0.f;                                             // lib.rs:1028
+            if (ok && !target_vec && uint32_t(c) == label) atomicAdd(&tail[1], -logf(fmaxf(p, 1e-12f)));  // lib.rs:611-615
+        }
+        if (mode & 4) { if (p >= best) { best = p; best_c = c; } }                // last maximal element wins
+        if ((mode & 8) && ok) atomicAdd(&sums[c], p);
+    }
+    if (mode & 4) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ob > best || (ob == best && oc > best_c)) { best = ob; best_c = oc; }
+        }
+        if (lane == 0 && best_c >= 0 && best >= threshold) atomicAdd(&hist[best_c], 1ull);  // lib.rs:1398-1400
+    }
+    if ((mode & 2) && lane == 0 && ok) atomicAdd(&tail[0], 1.f);
+}
+
+// Column sums of D[rows][cols] accumulated into g[cols] (bias gradients, lib.rs:1033,1038,1044).
+__global__ void colsum_kernel(const float* __restrict__ D, int rows, int cols, int ld, float* __restrict__ g, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += D[size_t(r) * ld + c];
+    atomicAdd(&g[c], acc);
+}
+
+// Gather rows perm[s..s+B) of feats, apply input dropout (lib.rs:119-129, no rescale), flag windows left all-zero
+// (lib.rs:607-609).  One warp per row.
+__global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_t* __restrict__ labels_all,
+                                  const uint32_t* __restrict__ perm, int B, int n_in, const uint8_t* __restrict__ keep,
+                                  int keep_by_row /* keep indexed by window id (1) or by batch row (0) */, float prob,
+                                  unsigned long long key, float* __restrict__ xb, uint32_t* __restrict__ lab,
+                                  uint8_t* __restrict__ valid) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const uint32_t w = perm ? perm[row] : uint32_t(row);
+    bool any = false;
+    for (int i = lane; i < n_in; i += 32) {
+        float v = feats[size_t(w) * n_in + i];
+        if (keep) {
+            if (!keep[size_t(keep_by_row ? w : uint32_t(row)) * n_in + i]) v = 0.f;
+        } else if (prob > 0.f) {
+            if (!dropout_keep(key, w, uint32_t(i), prob)) v = 0.f;
+        }
+        xb[size_t(row) * n_in + i] = v;
+        any |= (v != 0.f);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) {
+        valid[row] = any ? 1 : 0;
+        if (lab) lab[row] = labels_all ? labels_all[w] : 0xffffffffu;
+    }
+}
+
+// theta -= (lr / n_used) * g   (lib.rs:1047-1059); n_used comes from the (all-reduced) gradient tail.
+__global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__ grads, size_t n, float lr,
+                           double* __restrict__ stats) {
+    const float n_used = grads[n];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
+        stats[0] += double(grads[n + 1]);  // loss
+        stats[1] += double(n_used);
+    }
+    if (n_used <= 0.f) return;             // empty batch: no-op (lib.rs:1003-1005)
+    const float scale = lr / n_used;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        params[i] -= grads[i] * scale;
+}
+
+__global__ void init_uniform_kernel(float* __restrict__ w, size_t n, unsigned long long key, unsigned long long base) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const unsigned long long u = splitmix64(key ^ (base + i));
+        w[i] = float(uint32_t(u >> 40)) * 5.9604644775390625e-08f - 0.5f;  // U[-0.5, 0.5) (lib.rs:770)
+    }
+}
+
+szb_status net_reserve_rows(szb_net* net, uint64_t rows) {
+    if (rows <= net->cap_rows) return SZB_OK;
+    SZB_TRY(net->xb.reserve(rows * net->n_in * 4));
+    SZB_TRY(net->lab.reserve(rows * 4));
+    SZB_TRY(net->valid.reserve(rows));
+    SZB_TRY(net->a_h1.reserve(rows * net->h1 * 4));
+    SZB_TRY(net->a_h2.reserve(rows * net->h2 * 4));
+    SZB_TRY(net->a_z.reserve(rows * net->n_out * 4));
+    SZB_TRY(net->d_2.reserve(rows * net->h2 * 4));
+    SZB_TRY(net->d_1.reserve(rows * net->h1 * 4));
+    net->cap_rows = rows;
+    return SZB_OK;
+}
+
+// forward for rows already in d_x (device); leaves logits in a_z; activations in a_h1 / a_h2
+static szb_status forward_rows(szb_net* net, const float* d_x, int B) {
+    szb_ctx* ctx = net->ctx;
+    float* P = net->params.as<float>();
+    SZB_TRY((gemm<false, false, EPI_BIAS_RELU>(ctx, B, net->h1, net->n_in, d_x, net->n_in, P + net->off_w1(), net->h1,
+                                                net->a_h1.as<float>(), net->h1, P + net->off_b1(), nullptr, 0)));
+    SZB_TRY((gemm<false, false, EPI_BIAS_TANH>(ctx, B, net->h2, net->h1, net->a_h1.as<float>(), net->h1, P + net->off_w2(),
+                                                net->h2, net->a_h2.as<float>(), net->h2, P + net->off_b2(), nullptr, 0)));
+    SZB_TRY((gemm<false, false, EPI_BIAS>(ctx, B, net->n_out, net->h2, net->a_h2.as<float>(), net->h2, P + net->off_w3(),
+                                           net->n_out, net->a_z.as<float>(), net->n_out, P + net->off_b3(), nullptr, 0)));
+    return SZB_OK;
+}
+
+static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, const uint32_t* labels, const float* target_vec,
+                                 const uint8_t* valid, float threshold, unsigned long long* hist, float* sums) {
+    if (B <= 0) return SZB_OK;
+    const int wpb = 8;
+    float* tail = net->grads.as<float>() + net->n_params();
+    softmax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out),
+                                                                          int(net->n_out), mode, probs, labels, target_vec,
+                                                                          valid, tail, threshold, hist, sums);
+    SZB_CUDA(cudaGetLastError());
+    net->ctx->launches += 1;
+    return SZB_OK;
+}
+
+// One optimiser step on the B rows staged in net->xb (+ lab / valid): forward, CE backward, [all-reduce], SGD.
+szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n);  // comm.cu
+
+static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr) {
+    szb_ctx* ctx = net->ctx;
+    float* P = net->params.as<float>();
+    float* G = net->grads.as<float>();
+    const size_t np = net->n_params();
+    SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
+    if (B > 0) {
+        const float* xb = net->xb.as<float>();
+        SZB_TRY(forward_rows(net, xb, B));
+        SZB_TRY(launch_softmax(net, B, 2, nullptr, net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), 0.f, nullptr,
+                               nullptr));
+        float* d3 = net->a_z.as<float>();
+        const int C = int(net->n_out), H1 = int(net->h1), H2 = int(net->h2), I = int(net->n_in);
+        // layer 3
+        SZB_TRY((gemm<true, false, EPI_ATOMIC>(ctx, H2, C, B, net->a_h2.as<float>(), H2, d3, C, G + net->off_w3(), C, nullptr,
+                                                nullptr, 0)));
+        SZB_TRY((gemm<false, true, EPI_MUL_DTANH>(ctx, B, H2, C, d3, C, P + net->off_w3(), C, net->d_2.as<float>(), H2, nullptr,
+                                                   net->a_h2.as<float>(), H2)));
+        // layer 2
+        SZB_TRY((gemm<true, false, EPI_ATOMIC>(ctx, H1, H2, B, net->a_h1.as<float>(), H1, net->d_2.as<float>(), H2,
+                                                G + net->off_w2(), H2, nullptr, nullptr, 0)));
+        SZB_TRY((gemm<false, true, EPI_MUL_DRELU>(ctx, B, H1, H2, net->d_2.as<float>(), H2, P + net->off_w2(), H2,
+                                                   net->d_1.as<float>(), H1, nullptr, net->a_h1.as<float>(), H1)));
+        // layer 1
+        SZB_TRY((gemm<true, false, EPI_ATOMIC>(ctx, I, H1, B, xb, I, net->d_1.as<float>(), H1, G + net->off_w1(), H1, nullptr,
+                                                nullptr, 0)));
+        // bias gradients
+        auto colsum = [&](const float* D, int cols, float* g) -> szb_status {
+            const int rpb = 128;
+            dim3 grid((cols + 127) / 128, (B + rpb - 1) / rpb);
+            colsum_kernel<<<grid, 128, 0, ctx->stream>>>(D, B, cols, cols, g, rpb);
+            SZB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            return SZB_OK;
+        };
+        SZB_TRY(colsum(d3, C, G + net->off_b3()));
+        SZB_TRY(colsum(net->d_2.as<float>(), H2, G + net->off_b2()));
+        SZB_TRY(colsum(net->d_1.as<float>(), H1, G + net->off_b1()));
+    }
+    if (ctx->world > 1) SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
+    const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
+    sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, int B,
+                              const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key) {
+    if (B <= 0) return SZB_OK;
+    const int wpb = 8;
+    prep_batch_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(
+        d_feats, d_labels, d_perm, B, int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
+        net->lab.as<uint32_t>(), net->valid.as<uint8_t>());
+    SZB_CUDA(cudaGetLastError());
+    net->ctx->launches += 1;
+    return SZB_OK;
+}
+
+static szb_status net_alloc(szb_ctx* ctx, uint32_t n_in, uint32_t h1, uint32_t h2, uint32_t n_out, szb_net** out) {
+    SZB_REQUIRE(ctx && out, "net: NULL argument");
+    SZB_REQUIRE(n_in > 0 && h1 > 0 && h2 > 0 && n_out > 0, "net: layer sizes must be positive (%u,%u,%u,%u)", n_in, h1, h2, n_out);
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    szb_net* net = new szb_net();
+    net->ctx = ctx;
+    net->n_in = n_in; net->h1 = h1; net->h2 = h2; net->n_out = n_out;
+    szb_status s = net->params.reserve(net->n_params() * 4);
+    if (s == SZB_OK) s = net->grads.reserve((net->n_params() + kGradTail) * 4);
+    if (s == SZB_OK) s = net->stats.reserve(2 * sizeof(double));
+    if (s != SZB_OK) { szb_net_destroy(net); return s; }
+    cudaMemsetAsync(net->params.ptr, 0, net->n_params() * 4, ctx->stream);
+    cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream);
+    *out = net;
+    return SZB_OK;
+}
+
+}  // namespace szb
+
+using namespace szb;
+
+extern "C" {
+
+szb_status szb_net_create(szb_ctx* ctx, uint32_t n_in, uint32_t h1, uint32_t h2, uint32_t n_out, uint64_t seed, szb_net** out) {
+    SZB_TRY(net_alloc(ctx, n_in, h1, h2, n_out, out));
+    szb_net* net = *out;
+    const unsigned long long key = splitmix64(seed ^ 0x57A3A2B200ull);
+    float* P = net->params.as<float>();
+    struct { size_t off, n; } blocks[3] = { { net->off_w1(), size_t(n_in) * h1 }, { net->off_w2(), size_t(h1) * h2 },
+                                            { net->off_w3(), size_t(h2) * n_out } };
+    for (auto& b : blocks) {
+        init_uniform_kernel<<<int(std::min<size_t>((b.n + 255) / 256, 1024)), 256, 0, ctx->stream>>>(P + b.off, b.n, key, b.off);
+        SZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_net_from_weights(szb_ctx* ctx, uint32_t n_in, uint32_t h1, uint32_t h2, uint32_t n_out, const float* w1,
+                                const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                                szb_net** out) {
+    SZB_REQUIRE(w1 && b1 && w2 && b2 && w3 && b3, "szb_net_from_weights: NULL weights");
+    SZB_TRY(net_alloc(ctx, n_in, h1, h2, n_out, out));
+    szb_net* net = *out;
+    std::vector<float> flat(net->n_params());
+    std::memcpy(&flat[net->off_w1()], w1, size_t(n_in) * h1 * 4);
+    std::memcpy(&flat[net->off_b1()], b1, size_t(h1) * 4);
+    std::memcpy(&flat[net->off_w2()], w2, size_t(h1) * h2 * 4);
+    std::memcpy(&flat[net->off_b2()], b2, size_t(h2) * 4);
+    std::memcpy(&flat[net->off_w3()], w3, size_t(h2) * n_out * 4);
+    std::memcpy(&flat[net->off_b3()], b3, size_t(n_out) * 4);
+    SZB_CUDA(cudaMemcpyAsync(net->params.ptr, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_net_get_weights(szb_net* net, float* w1, float* b1, float* w2, float* b2, float* w3, float* b3) {
+    SZB_REQUIRE(net, "szb_net_get_weights: net is NULL");
+    std::vector<float> flat(net->n_params());
+    SZB_CUDA(cudaSetDevice(net->ctx->device));
+    SZB_CUDA(cudaMemcpyAsync(flat.data(), net->params.ptr, flat.size() * 4, cudaMemcpyDeviceToHost, net->ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    if (w1) std::memcpy(w1, &flat[net->off_w1()], size_t(net->n_in) * net->h1 * 4);
+    if (b1) std::memcpy(b1, &flat[net->off_b1()], size_t(net->h1) * 4);
+    if (w2) std::memcpy(w2, &flat[net->off_w2()], size_t(net->h1) * net->h2 * 4);
+    if (b2) std::memcpy(b2, &flat[net->off_b2()], size_t(net->h2) * 4);
+    if (w3) std::memcpy(w3, &flat[net->off_w3()], size_t(net->h2) * net->n_out * 4);
+    if (b3) std::memcpy(b3, &flat[net->off_b3()], size_t(net->n_out) * 4);
+    return SZB_OK;
+}
+
+szb_status szb_net_dims(const szb_net* net, uint32_t dims[4]) {
+    SZB_REQUIRE(net && dims, "szb_net_dims: NULL argument");
+    dims[0] = net->n_in; dims[1] = net->h1; dims[2] = net->h2; dims[3] = net->n_out;
+    return SZB_OK;
+}
+uint32_t szb_net_output_size(const szb_net* net) { return net ? net->n_out : 0; }
+
+szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t seed) {
+    SZB_REQUIRE(net, "szb_net_add_output_class: net is NULL");
+    const uint32_t C = net->n_out, H2 = net->h2;
+    std::vector<float> w1(size_t(net->n_in) * net->h1), b1(net->h1), w2(size_t(net->h1) * H2), b2(H2), w3(size_t(H2) * C), b3(C);
+    SZB_TRY(szb_net_get_weights(net, w1.data(), b1.data(), w2.data(), b2.data(), w3.data(), b3.data()));
+    std::vector<float> nw3(size_t(H2) * (C + 1)), nb3(C + 1, 0.f);
+    const unsigned long long key = splitmix64(seed ^ 0xADD0C1A55ull);
+    for (uint32_t r = 0; r < H2; ++r) {
+        for (uint32_t c = 0; c < C; ++c) nw3[size_t(r) * (C + 1) + c] = w3[size_t(r) * C + c];   // lib.rs:803-806
+        nw3[size_t(r) * (C + 1) + C] = new_col ? new_col[r]                                         // lib.rs:807-809
+                                               : float(uint32_t(splitmix64(key ^ r) >> 40)) * 5.9604644775390625e-08f - 0.5f;
+    }
+    for (uint32_t c = 0; c < C; ++c) nb3[c] = b3[c];                                                // lib.rs:812-815
+    szb_net* fresh = nullptr;
+    SZB_TRY(szb_net_from_weights(net->ctx, net->n_in, net->h1, H2, C + 1, w1.data(), b1.data(), w2.data(), b2.data(), nw3.data(),
+                                 nb3.data(), &fresh));
+    // adopt the new buffers in place so the caller's handle stays valid
+    net->params.release(); net->grads.release();
+    net->params = fresh->params; net->grads = fresh->grads;
+    fresh->params = DevBuf(); fresh->grads = DevBuf();
+    net->n_out = C + 1;
+    net->a_z.release(); net->cap_rows = 0;
+    szb_net_destroy(fresh);
+    return SZB_OK;
+}
+
+void szb_net_destroy(szb_net* net) {
+    if (!net) return;
+    if (net->ctx) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); }
+    for (DevBuf* b : { &net->params, &net->grads, &net->xb, &net->lab, &net->valid, &net->a_h1, &net->a_h2, &net->a_z, &net->d_2,
+                       &net->d_1, &net->stats, &net->perm, &net->hist })
+        b->release();
+    delete net;
+}
+
+// Rows are processed in chunks so the activation scratch stays bounded.
+static constexpr uint64_t kChunkRows = 1u << 16;
+
+szb_status szb_net_forward_dev(szb_net* net, const float* d_x, uint64_t B, float* d_probs) {
+    SZB_REQUIRE(net, "szb_net_forward_dev: net is NULL");
+    if (B == 0) return SZB_OK;
+    SZB_REQUIRE(d_x && d_probs, "szb_net_forward_dev: NULL buffer");
+    SZB_CUDA(cudaSetDevice(net->ctx->device));
+    SZB_TRY(net_reserve_rows(net, std::min(B, kChunkRows)));
+    for (uint64_t r0 = 0; r0 < B; r0 += kChunkRows) {
+        const int nb = int(std::min(kChunkRows, B - r0));
+        SZB_TRY(forward_rows(net, d_x + r0 * net->n_in, nb));
+        SZB_TRY(launch_softmax(net, nb, 1, d_probs + r0 * net->n_out, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr));
+    }
+    return SZB_OK;
+}
+
+szb_status szb_net_forward(szb_net* net, const float* x, uint64_t B, float* probs) {
+    SZB_REQUIRE(net, "szb_net_forward: net is NULL");
+    if (B == 0) return SZB_OK;
+    SZB_REQUIRE(x && probs, "szb_net_forward: NULL buffer");
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->x.reserve(B * net->n_in * 4));
+    SZB_TRY(ctx->probs.reserve(B * net->n_out * 4));
+    SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, x, B * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(szb_net_forward_dev(net, ctx->x.as<float>(), B, ctx->probs.as<float>()));
+    SZB_CUDA(cudaMemcpyAsync(probs, ctx->probs.ptr, B * net->n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+static szb_status read_stats(szb_net* net, double* loss_sum, uint64_t* n_used) {
+    double h[2] = { 0, 0 };
+    SZB_CUDA(cudaMemcpyAsync(h, net->stats.ptr, sizeof h, cudaMemcpyDeviceToHost, net->ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    if (loss_sum) *loss_sum = h[0];
+    if (n_used) *n_used = uint64_t(h[1] + 0.5);
+    return SZB_OK;
+}
+
+szb_status szb_net_train_batch(szb_net* net, const float* x, uint64_t B, const float* target, float lr) {
+    SZB_REQUIRE(net, "szb_net_train_batch: net is NULL");
+    if (B == 0) return SZB_OK;  // lib.rs:1003-1005
+    SZB_REQUIRE(x && target, "szb_net_train_batch: NULL buffer");
+    SZB_REQUIRE(B <= (1u << 24), "szb_net_train_batch: batch of %llu rows is too large", (unsigned long long)B);
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(net_reserve_rows(net, B));
+    SZB_TRY(ctx->probs.reserve(size_t(net->n_out) * 4));
+    SZB_CUDA(cudaMemcpyAsync(net->xb.ptr, x, B * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemcpyAsync(ctx->probs.ptr, target, size_t(net->n_out) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemsetAsync(net->valid.ptr, 1, B, ctx->stream));  // the reference's train_batch uses every row it is given
+    SZB_TRY(train_step_staged(net, int(B), ctx->probs.as<float>(), lr));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_net_train_batch_labels(szb_net* net, const float* x, const uint32_t* labels, uint64_t B, float lr,
+                                      const uint8_t* keep, double* loss_sum, uint64_t* n_used) {
+    SZB_REQUIRE(net, "szb_net_train_batch_labels: net is NULL");
+    if (loss_sum) *loss_sum = 0.0;
+    if (n_used) *n_used = 0;
+    if (B == 0) return SZB_OK;
+    SZB_REQUIRE(x && labels, "szb_net_train_batch_labels: NULL buffer");
+    SZB_REQUIRE(B <= (1u << 24), "szb_net_train_batch_labels: batch of %llu rows is too large", (unsigned long long)B);
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(net_reserve_rows(net, B));
+    SZB_TRY(ctx->x.reserve(B * net->n_in * 4));
+    SZB_TRY(ctx->labels.reserve(B * 4));
+    SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, x, B * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, labels, B * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* d_keep = nullptr;
+    if (keep) {
+        SZB_TRY(ctx->misc.reserve(B * net->n_in));
+        SZB_CUDA(cudaMemcpyAsync(ctx->misc.ptr, keep, B * net->n_in, cudaMemcpyHostToDevice, ctx->stream));
+        d_keep = ctx->misc.as<uint8_t>();
+    }
+    SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
+    SZB_TRY(launch_prep(net, ctx->x.as<float>(), ctx->labels.as<uint32_t>(), nullptr, int(B), d_keep, 0, 0.f, 0));
+    SZB_TRY(train_step_staged(net, int(B), nullptr, lr));
+    return read_stats(net, loss_sum, n_used);
+}
+
+szb_status szb_net_train_epoch_dev(szb_net* net, const float* d_feats, const uint32_t* d_labels, uint64_t n,
+                                   const uint32_t* perm, uint64_t n_perm, uint32_t batch, float lr, float dropout, uint64_t seed,
+                                   uint64_t stream, const uint8_t* d_keep, double* loss_sum, uint64_t* n_used) {
+    SZB_REQUIRE(net, "szb_net_train_epoch_dev: net is NULL");
+    if (loss_sum) *loss_sum = 0.0;
+    if (n_used) *n_used = 0;
+    if (n_perm == 0) return SZB_OK;
+    SZB_REQUIRE(d_feats && d_labels && perm, "szb_net_train_epoch_dev: NULL buffer");
+    SZB_REQUIRE(n <= 0xffffffffull, "szb_net_train_epoch_dev: more than 2^32 windows");
+    if (batch == 0) batch = 1;  // lib.rs:602 batch_size.max(1)
+    for (uint64_t i = 0; i < n_perm; ++i)
+        SZB_REQUIRE(perm[i] < n, "szb_net_train_epoch_dev: perm[%llu] = %u out of range", (unsigned long long)i, perm[i]);
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(net_reserve_rows(net, batch));
+    SZB_TRY(net->perm.reserve(n_perm * 4));
+    SZB_CUDA(cudaMemcpyAsync(net->perm.ptr, perm, n_perm * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
+    const unsigned long long key = dropout_key(seed, stream);
+    for (uint64_t s = 0; s < n_perm; s += batch) {
+        const int B = int(std::min<uint64_t>(batch, n_perm - s));
+        SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
+        SZB_TRY(train_step_staged(net, B, nullptr, lr));
+    }
+    return read_stats(net, loss_sum, n_used);
+}
+
+szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t* rows, uint64_t n_rows, uint32_t n_in, float prob,
+                                 uint8_t* keep) {
+    SZB_REQUIRE(keep && (rows || n_rows == 0), "szb_dropout_keep_mask: NULL argument");
+    SZB_REQUIRE(n_in <= 64, "szb_dropout_keep_mask: n_in %u > 64 (the counter packs the feature index in 6 bits)", n_in);
+    const unsigned long long key = dropout_key(seed, stream);
+    for (uint64_t r = 0; r < n_rows; ++r)
+        for (uint32_t i = 0; i < n_in; ++i)
+            keep[r * n_in + i] = (prob <= 0.f || dropout_keep(key, rows[r], i, prob)) ? 1 : 0;
+    return SZB_OK;
+}
+
+// ---- aggregation ----------------------------------------------------------------------------------------------------
+static szb_status identify_dev(szb_net* net, const float* d_feats, uint64_t n, float threshold, uint64_t* counts, float* sums) {
+    szb_ctx* ctx = net->ctx;
+    const uint32_t C = net->n_out;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(net->hist.reserve(size_t(C) * (8 + 4)));
+    unsigned long long* d_hist = net->hist.as<unsigned long long>();
+    float* d_sums = reinterpret_cast<float*>(d_hist + C);
+    SZB_CUDA(cudaMemsetAsync(net->hist.ptr, 0, size_t(C) * 12, ctx->stream));
+    if (n > 0) {
+        SZB_TRY(net_reserve_rows(net, std::min(n, kChunkRows)));
+        for (uint64_t r0 = 0; r0 < n; r0 += kChunkRows) {
+            const int nb = int(std::min(kChunkRows, n - r0));
+            SZB_TRY(forward_rows(net, d_feats + r0 * net->n_in, nb));
+            SZB_TRY(launch_softmax(net, nb, counts ? 4 : 8, nullptr, nullptr, nullptr, nullptr, threshold, d_hist, d_sums));
+        }
+    }
+    if (counts) SZB_CUDA(cudaMemcpyAsync(counts, d_hist, size_t(C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sums) SZB_CUDA(cudaMemcpyAsync(sums, d_sums, size_t(C) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
+szb_status szb_identify_counts_dev(szb_net* net, const float* d_feats, uint64_t n, float threshold, uint64_t* counts) {
+    SZB_REQUIRE(net && counts && (d_feats || n == 0), "szb_identify_counts_dev: NULL argument");
+    return identify_dev(net, d_feats, n, threshold, counts, nullptr);
+}
+
+szb_status szb_identify_counts(szb_net* net, const float* feats, uint64_t n, float threshold, uint64_t* counts) {
+    SZB_REQUIRE(net && counts && (feats || n == 0), "szb_identify_counts: NULL argument");
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    if (n) {
+        SZB_TRY(ctx->x.reserve(n * net->n_in * 4));
+        SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, feats, n * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return identify_dev(net, ctx->x.as<float>(), n, threshold, counts, nullptr);
+}
+
+szb_status szb_identify_sums(szb_net* net, const float* feats, uint64_t n, float* sums) {
+    SZB_REQUIRE(net && sums && (feats || n == 0), "szb_identify_sums: NULL argument");
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    if (n) {
+        SZB_TRY(ctx->x.reserve(n * net->n_in * 4));
+        SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, feats, n * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return identify_dev(net, ctx->x.as<float>(), n, 0.f, nullptr, sums);
+}
+
+szb_status szb_identify_speaker_list(szb_net* net, const int16_t* pcm, uint64_t n_samples, float threshold, uint32_t* speakers,
+                                     uint32_t cap, uint32_t* n_speakers) {
+    SZB_REQUIRE(net && n_speakers, "szb_identify_speaker_list: NULL argument");
+    SZB_REQUIRE(net->n_in == SZB_FEATURE_SIZE, "szb_identify_speaker_list: net input size %u != 60", net->n_in);
+    szb_ctx* ctx = net->ctx;
+    *n_speakers = 0;
+    const uint64_t n = szb_num_windows(n_samples);
+    std::vector<uint64_t> counts(net->n_out, 0);
+    if (n > 0) {
+        SZB_REQUIRE(pcm, "szb_identify_speaker_list: pcm is NULL");
+        SZB_CUDA(cudaSetDevice(ctx->device));
+        // extraction output stays on the device and feeds the forward pass directly (lib.rs:1390-1392)
+        SZB_TRY(ctx->pcm.reserve(n_samples * 2 + 64));
+        SZB_TRY(ctx->feats.reserve(n * SZB_FEATURE_SIZE * 4));
+        SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, pcm, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
+        const uint64_t off[2] = { 0, n_samples };
+        uint64_t woff[2];
+        SZB_TRY(szb_extract_batch_dev(ctx, ctx->pcm.as<int16_t>(), off, 1, SZB_SAMPLE_RATE, ctx->feats.as<float>(), n, woff));
+        SZB_TRY(identify_dev(net, ctx->feats.as<float>(), n, threshold, counts.data(), nullptr));
+    }
+    // lib.rs:1403-1410: keep count > 0, stable sort by count descending
+    std::vector<std::pair<uint32_t, uint64_t>> pairs;
+    for (uint32_t c = 0; c < net->n_out; ++c)
+        if (counts[c] > 0) pairs.emplace_back(c, counts[c]);
+    std::stable_sort(pairs.begin(), pairs.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    *n_speakers = uint32_t(pairs.size());
+    SZB_REQUIRE(cap >= pairs.size() && (speakers || pairs.empty()), "szb_identify_speaker_list: capacity %u < %zu", cap, pairs.size());
+    for (size_t i = 0; i < pairs.size(); ++i) speakers[i] = pairs[i].first;
+    return SZB_OK;
+}
+
+}  // extern "C"
