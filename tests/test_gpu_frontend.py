@@ -1,0 +1,150 @@
+"""Parity of the CUDA front end against the oracle and the golden fixtures, through the C ABI (ctypes).
+Tolerance: max-abs 1e-4 on normalised MFCC+delta features against the float64 oracle (BASELINE.json north_star);
+the resampler + quantisation is integer-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _check(sz_ex, oracle, clip):
+    got = sz_ex.extract(clip)
+    want = oracle.extract(clip)
+    assert got.shape == want.shape and got.dtype == np.float32
+    if len(want):
+        assert np.abs(got - want).max() <= TOL
+    return got
+
+
+@pytest.fixture(scope="module")
+def ex(sz, ctx):
+    return sz.FeatureExtractor(ctx)
+
+
+def test_golden_fixtures(ex, golden):
+    for name in ("a", "b"):
+        got = ex.extract(golden[f"clip_{name}_i16"])
+        assert got.shape == golden[f"clip_{name}_features_f64"].shape
+        assert np.abs(got - golden[f"clip_{name}_features_f64"]).max() <= TOL
+
+
+@pytest.mark.parametrize("n", [0, 1, 799, 800, 801, 1199, 1200, 1201, 1999, 2000, 800 + 400 * 31, 800 + 400 * 32, 800 + 400 * 33,
+                               800 + 400 * 63 + 399, 800 + 400 * 64, 44100])
+def test_edge_lengths(ex, oracle, n):
+    clip = oracle.synth_clip(n % 5, n, max(n, 1) / 44100.0)[:n]
+    got = _check(ex, oracle, clip)
+    assert got.shape[0] == oracle.n_windows(n)          # short input -> empty, no error (lib.rs:289)
+
+
+def test_silence_and_extremes(ex, oracle):
+    f = ex.extract(np.zeros(800 + 400 * 5, np.int16))
+    assert np.allclose(f[:, 0], -7.681146, atol=1e-5) and np.allclose(f[:, 1:], 0.1301889, atol=1e-6)
+    # full-scale inputs (|x| up to 32768, frame sums up to 2.6e7) with energy in every mel band.  A signal whose
+    # spectrum is exactly zero in some band (e.g. a bin-periodic square wave) is NOT a parity case: ln() of pure
+    # float32 rounding noise is arbitrary in the reference itself (DESIGN.md "Conditioning").
+    r = np.random.default_rng(0)
+    _check(ex, oracle, r.integers(-32768, 32768, 44100).astype(np.int16))
+    loud = np.where(r.random(20000) < 0.5, 32767, -32768).astype(np.int16)
+    _check(ex, oracle, loud)
+    quiet = (oracle.synth_clip(1, 3, 0.5) // 2000).astype(np.int16)               # a few LSBs of signal
+    _check(ex, oracle, quiet)
+
+
+def test_five_second_and_sixty_second_clips(ex, oracle):
+    c5 = oracle.synth_clip(2, 5, 5.0)
+    assert _check(ex, oracle, c5).shape == (550, 60)
+    c60 = np.concatenate([oracle.synth_clip(s, 60 + s, 15.0) for s in range(4)])   # mixed-speaker 60 s clip (C5)
+    assert _check(ex, oracle, c60).shape == (6614, 60)
+
+
+def test_ragged_batch_with_empty_and_misaligned_clips(ex, oracle):
+    lens = [0, 13001, 799, 800, 44100, 2403, 1, 30000, 17777]
+    clips = [oracle.synth_clip(i % 4, 100 + i, max(l, 1) / 44100.0)[:l] for i, l in enumerate(lens)]
+    outs = ex.extract_batch(clips)
+    for o, c in zip(outs, clips):
+        w = oracle.extract(c)
+        assert o.shape == w.shape
+        if len(w):
+            assert np.abs(o - w).max() <= TOL
+
+
+def test_segmented_long_clip_is_bit_identical_to_single_clip_path(ex, oracle):
+    # a clip alone in a batch is split into many window-range segments (halo recompute at the cuts); inside a
+    # large batch it is one segment.  Both must produce the same bits.
+    clip = oracle.synth_clip(3, 77, 8.0)
+    alone = ex.extract(clip)
+    filler = [oracle.synth_clip(i % 3, i, 8.0) for i in range(700)]
+    in_batch = ex.extract_batch(filler[:350] + [clip] + filler[350:])[350]
+    assert np.array_equal(alone, in_batch)
+
+
+def test_linearity_in_gain_shifts_only_c0(ex, oracle):
+    # size-independent property: doubling the signal adds ln 4 to every mel energy, i.e. 26 ln 4 to c0 only
+    clip = (oracle.synth_clip(1, 9, 2.0) // 4).astype(np.int16)
+    a, b = oracle.mfcc_frames(clip), oracle.mfcc_frames((clip * 2).astype(np.int16))
+    assert np.allclose(b[:, 0] - a[:, 0], 26 * np.log(4.0), atol=1e-6) and np.allclose(b[:, 1:], a[:, 1:], atol=1e-6)
+    fa, fb = ex.extract(clip), ex.extract((clip * 2).astype(np.int16))
+    wa, wb = oracle.extract(clip), oracle.extract((clip * 2).astype(np.int16))
+    assert np.abs((fb - fa) - (wb - wa)).max() <= 2 * TOL
+
+
+def test_rows_are_z_scored(ex, oracle):
+    f = ex.extract(oracle.synth_clip(0, 1, 10.0)).astype(np.float64)
+    assert f.shape == (1101, 60)
+    assert np.abs(f.mean(axis=1)).max() < 1e-5 and np.abs(f.std(axis=1) - 1).max() < 1e-4
+
+
+def test_downmix(sz, ctx, oracle):
+    r = np.random.default_rng(0)
+    for ch, n in ((2, 20001), (3, 999), (6, 12000), (1, 100)):
+        s = r.integers(-32768, 32768, n).astype(np.int16)
+        assert np.array_equal(sz.downmix_to_mono(s, ch, ctx), oracle.downmix_to_mono(s, ch))
+
+
+@pytest.mark.parametrize("rate", [8000, 11025, 16000, 22050, 32000, 48000])
+def test_resampler_is_bit_exact(sz, ctx, oracle, native, rate):
+    x = oracle.synth_clip(2, rate, 0.7, rate=rate)
+    L, M = oracle.resample_ratio(rate)
+    taps = np.zeros((L, 16), np.float32)
+    native.check(native.lib.szb_table_resample_taps(rate, taps.ctypes.data_as(C.c_void_p), None, None))
+    got = sz.resample_to_44100(x, rate, ctx)
+    assert got.dtype == np.int16 and len(got) == len(x) * 44100 // rate            # lib.rs:196
+    assert np.array_equal(got, oracle.resample_to_44100(x, rate, taps))            # same taps -> same bits
+    indep = oracle.resample_to_44100(x, rate)                                      # oracle's own taps
+    assert np.abs(got.astype(int) - indep.astype(int)).max() <= 1
+    assert (got != indep).mean() < 1e-3
+    loud = np.where(np.arange(3000) % 40 < 20, 32767, -32768).astype(np.int16)     # overshoot must clamp (lib.rs:207)
+    assert np.array_equal(sz.resample_to_44100(loud, rate, ctx), oracle.resample_to_44100(loud, rate, taps))
+
+
+def test_resample_identity_and_empty(sz, ctx):
+    s = np.arange(-50, 50, dtype=np.int16)
+    assert np.array_equal(sz.resample_to_44100(s, 44100, ctx), s)                  # lib.rs:187-189
+    assert len(sz.resample_to_44100(np.zeros(0, np.int16), 16000, ctx)) == 0
+
+
+@pytest.mark.parametrize("rate", [16000, 32000, 48000])
+def test_batch_from_other_rates_equals_resample_then_extract(sz, ctx, ex, oracle, rate):
+    clips = [oracle.synth_clip(i % 3, 200 + i, 0.4 + 0.37 * i, rate=rate) for i in range(5)] + [np.zeros(10, np.int16)]
+    outs = ex.extract_batch(clips, rate=rate)
+    for o, c in zip(outs, clips):
+        r = sz.resample_to_44100(c, rate, ctx)
+        assert np.array_equal(o, ex.extract(r))                                    # fused path == API composition, bit for bit
+        w = oracle.extract(r)
+        assert o.shape == w.shape
+        if len(w):
+            assert np.abs(o - w).max() <= TOL
+
+
+def test_capacity_and_argument_errors(sz, ctx, native, oracle):
+    clip = oracle.synth_clip(0, 0, 0.5)
+    out = np.zeros((3, 60), np.float32)
+    n = C.c_uint64()
+    st = native.lib.szb_extract(ctx.handle, clip.ctypes.data_as(C.c_void_p), len(clip), out.ctypes.data_as(C.c_void_p), 3, C.byref(n))
+    assert st == native.ERR_INVALID and b"capacity" in native.lib.szb_last_error()
+    assert n.value == oracle.n_windows(len(clip))                                   # size is still reported
+    assert native.lib.szb_resample_to_44100(ctx.handle, None, 0, 0, None, 0, C.byref(n)) == native.ERR_INVALID

@@ -1,0 +1,201 @@
+"""Parity of the SimpleNeuralNet kernels and the aggregation against the oracle, through the C ABI.
+Tolerances (FP32 path): probabilities max-abs 1e-5; weights after one step max-abs 1e-5; after an epoch 1e-4;
+identical argmax labels and identical per-class counts."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(sz, ctx, oracle, dims, seed=0):
+    onet = oracle.Net.init(*dims, seed=seed)
+    onet.b1[:] = np.random.default_rng(seed).uniform(-.1, .1, dims[1])
+    onet.b2[:] = np.random.default_rng(seed + 1).uniform(-.1, .1, dims[2])
+    onet.b3[:] = np.random.default_rng(seed + 2).uniform(-.1, .1, dims[3])
+    return onet, sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+
+
+def _werr(net, onet):
+    return max(float(np.abs(a - b).max()) for a, b in zip(net.weights(), onet.params()))
+
+
+@pytest.mark.parametrize("dims,B", [((60, 512, 256, 100), 300), ((60, 512, 256, 2), 64), ((60, 512, 256, 1000), 33),
+                                    ((4, 3, 2, 2), 5), ((60, 512, 256, 1), 7), ((17, 33, 65, 9), 130)])
+def test_forward(sz, ctx, oracle, dims, B):
+    onet, net = _pair(sz, ctx, oracle, dims, seed=B)
+    x = np.random.default_rng(B).standard_normal((B, dims[0])).astype(np.float32)
+    p, q = net.forward(x), oracle.forward(onet, x)
+    assert p.shape == q.shape and np.abs(p - q).max() <= 1e-5
+    assert np.abs(p.sum(axis=1) - 1).max() < 1e-5
+    q64 = oracle.forward(onet.copy(np.float64), x)
+    margin = np.sort(q64, axis=1)[:, -1] - (np.sort(q64, axis=1)[:, -2] if dims[3] > 1 else 0)
+    clear = margin > 1e-4
+    assert np.array_equal(p.argmax(axis=1)[clear], q64.argmax(axis=1)[clear])       # identical labels off near-ties
+    assert np.abs(net.forward(x[0]) - p[0]).max() <= 1e-7                           # single-window call
+
+
+def test_reference_unit_test_weights_change(sz, ctx):
+    # lib.rs:1832-1851
+    net = sz.SimpleNeuralNet(4, 3, 2, 2, seed=3, ctx=ctx)
+    before = net.weights()
+    assert all(np.all(b == 0) for b in (before[1], before[3], before[5]))           # zero biases (lib.rs:772-777)
+    assert all(np.abs(w).max() <= 0.5 and np.abs(w).max() > 0 for w in (before[0], before[2], before[4]))
+    net.train_batch([[0.1, -0.2, 0.3, 0.4]], [1.0, 0.0], 0.1)
+    after = net.weights()
+    assert any(np.any(a != b) for a, b in zip(before[:4], after[:4])), "weights did not change after training step"
+
+
+@pytest.mark.parametrize("dims,B", [((60, 512, 256, 100), 8), ((60, 512, 256, 100), 4096), ((4, 3, 2, 2), 1), ((60, 512, 256, 3), 577)])
+def test_train_batch_shared_target(sz, ctx, oracle, dims, B):
+    onet, net = _pair(sz, ctx, oracle, dims, seed=B)
+    x = np.random.default_rng(B).standard_normal((B, dims[0])).astype(np.float32)
+    t = np.zeros(dims[3], np.float32); t[dims[3] // 2] = 1
+    net.train_batch(x, t, 0.01); oracle.train_batch(onet, x, t, 0.01)
+    assert _werr(net, onet) <= 1e-5
+    soft = np.random.default_rng(1).dirichlet(np.ones(dims[3])).astype(np.float32)   # any target vector, not only one-hot
+    net.train_batch(x, soft, 0.05); oracle.train_batch(onet, x, soft, 0.05)
+    assert _werr(net, onet) <= 2e-5
+    net.train_batch(np.zeros((0, dims[0]), np.float32), t, 0.01)                    # empty batch: no-op (lib.rs:1003)
+    net.train(x[0], t, 0.01); oracle.train_batch(onet, x[:1], t, 0.01)              # train == batch of one (lib.rs:954)
+    assert _werr(net, onet) <= 3e-5
+
+
+def test_train_batch_labels_dropout_and_skip(sz, ctx, oracle):
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 10), seed=4)
+    r = np.random.default_rng(4)
+    x = r.standard_normal((64, 60)).astype(np.float32)
+    labels = r.integers(0, 12, 64).astype(np.uint32)              # 10, 11 >= n_out -> all-zero target (lib.rs:592-595)
+    keep = r.random((64, 60)) >= 0.2
+    keep[5] = False                                               # window left all-zero -> skipped (lib.rs:607-609)
+    x[9] = 0
+    loss, used = net.train_batch_labels(x, labels, 0.01, keep)
+    oloss, oused = oracle.train_epoch(onet, x, labels, np.arange(64), 64, 0.01, keep)
+    assert used == oused == 62
+    assert abs(loss - oloss) <= 1e-3 * max(1.0, abs(oloss))
+    assert _werr(net, onet) <= 1e-5
+
+
+def test_epoch_with_library_dropout_stream(sz, ctx, oracle):
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 7), seed=9)
+    r = np.random.default_rng(9)
+    n = 1000
+    feats = r.standard_normal((n, 60)).astype(np.float32)
+    labels = r.integers(0, 7, n).astype(np.uint32)
+    data = sz.DeviceFeatures(ctx, feats, labels)
+    tot, cnt = 0.0, 0
+    for epoch in range(2):
+        perm = r.permutation(n).astype(np.uint32)
+        loss, used = sz.train_epoch(net, data, perm, 96, 0.02, dropout=0.2, seed=77, stream=epoch)   # 96 does not divide 1000
+        keep = oracle.dropout_keep_mask(77, epoch, np.arange(n), 60, 0.2)
+        oloss, oused = oracle.train_epoch(onet, feats, labels, perm, 96, 0.02, keep)
+        assert used == oused == n
+        assert abs(loss - oloss) <= 1e-3 * abs(oloss)
+    data.close()
+    assert _werr(net, onet) <= 1e-4
+
+
+def test_pretrain_from_features_reduces_loss(sz, ctx, oracle):
+    # C1-shaped: windows of two synthetic speakers, file-sequential training as train_from_feature_map (lib.rs:632-665)
+    ex = sz.FeatureExtractor(ctx)
+    fmap = {f"spk{s}_{i}.wav": ex.extract(oracle.synth_clip(s, 10 * s + i, 1.0)) for s in range(2) for i in range(2)}
+    files = [(p, int(p[3])) for p in sorted(fmap)]
+    net = sz.SimpleNeuralNet(60, 512, 256, 2, seed=1, ctx=ctx)
+    first = sz.train_from_feature_map(net, fmap, files, 1, 0.01, 0.2, 8, seed=1)
+    later = sz.train_from_feature_map(net, fmap, files, 3, 0.01, 0.2, 8, seed=2)
+    assert np.isfinite(first) and later < first
+    assert net.file_lists() == [["spk0_0.wav", "spk0_1.wav"], ["spk1_0.wav", "spk1_1.wav"]]
+    assert sz.pretrain_from_features(net, np.zeros((0, 60), np.float32), 0, 2, 3, 0.01, 0.2, 8) == 0.0   # lib.rs:623-627
+
+
+def test_identify_counts_sums_and_list(sz, ctx, oracle):
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 6), seed=12)
+    clip = np.concatenate([oracle.synth_clip(s, 40 + s, 2.0) for s in range(3)])
+    feats = oracle.extract(clip).astype(np.float32)
+    p64 = oracle.forward(onet.copy(np.float64), feats)
+    thr = 0.5
+    near = np.abs(p64.max(axis=1) - thr) < 1e-4
+    srt = np.sort(p64, axis=1)
+    near |= (srt[:, -1] - srt[:, -2]) < 1e-4
+    assert near.sum() == 0, "test data has a near-tie; change the seed"
+    counts = sz.identify_counts(net, feats, thr)
+    assert np.array_equal(counts, oracle.identify_counts(onet, feats, thr))
+    sums = sz.identify_sums(net, feats)
+    assert np.abs(sums - oracle.identify_sums(onet, feats)).max() <= 1e-3
+    ex = sz.FeatureExtractor(ctx)
+    assert sz.identify_speaker_list(net, clip, thr) == oracle.identify_speaker_list(onet, clip, thr)
+    assert sz.identify_speaker_list(net, clip[:500], thr) == []                      # no windows -> empty list
+    assert sz.identify_speaker(net, clip, ex) == oracle.identify_speaker(onet, feats)
+    assert sz.identify_speaker_with_threshold(net, clip, 0.0, ex) == oracle.identify_speaker_with_threshold_feats(onet, feats, 0.0)
+    assert sz.identify_speaker_with_threshold(net, clip, 1.1, ex) is None
+    one = sz.SimpleNeuralNet(60, 512, 256, 1, ctx=ctx)
+    assert sz.identify_speaker_with_threshold(one, clip, 0.0, ex) is None            # lib.rs:1316-1318
+    assert sz.identify_speaker_with_threshold_feats(net, feats[:0], 0.0) is None     # lib.rs:1363-1365
+
+
+def test_tie_break_takes_last_index(sz, ctx):
+    # identical output columns -> equal probabilities -> the LAST index is counted (lib.rs:1393-1396)
+    r = np.random.default_rng(0)
+    w3 = np.repeat(r.uniform(-.5, .5, (256, 1)).astype(np.float32), 4, axis=1)
+    net = sz.SimpleNeuralNet.from_weights(r.uniform(-.5, .5, (60, 512)), np.zeros(512), r.uniform(-.5, .5, (512, 256)), np.zeros(256),
+                                          w3, np.zeros(4), ctx=ctx)
+    feats = r.standard_normal((50, 60)).astype(np.float32)
+    assert sz.identify_counts(net, feats, 0.25).tolist() == [0, 0, 0, 50]
+    assert sz.identify_counts(net, feats, 0.26).tolist() == [0, 0, 0, 0]             # `>=` threshold (lib.rs:1398)
+
+
+def test_add_output_class(sz, ctx, oracle):
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 3), seed=2)
+    col = np.random.default_rng(5).uniform(-.5, .5, 256).astype(np.float32)
+    net.add_output_class(col)
+    w = net.weights()
+    assert net.output_size() == 4 and w[4].shape == (256, 4) and w[5].shape == (4,)
+    assert np.array_equal(w[4][:, :3], onet.w3) and np.array_equal(w[4][:, 3], col)  # lib.rs:803-809
+    assert np.array_equal(w[5][:3], onet.b3) and w[5][3] == 0                         # lib.rs:812-815
+    net.add_output_class()                                                            # random column in [-0.5, 0.5)
+    w = net.weights()
+    assert net.output_size() == 5 and np.abs(w[4][:, 4]).max() <= 0.5 and np.abs(w[4][:, 4]).max() > 0
+    x = np.random.default_rng(1).standard_normal((9, 60)).astype(np.float32)
+    assert net.forward(x).shape == (9, 5)
+
+
+def test_model_npz_round_trip_and_numpy_compat(sz, ctx, oracle, tmp_path):
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 5), seed=8)
+    net.record_training_file(0, "a/x.wav"); net.record_training_file(0, "a/y.wav"); net.record_training_file(0, "a/x.wav")
+    net.record_training_file(3, "b/z.mp3")
+    path = str(tmp_path / "model.npz")
+    net.save(path)
+    z = np.load(path)                                                                # numpy reads the reference's layout
+    names = set(z.files)
+    assert {"w1", "b1", "w2", "b2", "sample_rate", "bits", "num_speakers", "w3_1", "b3_5", "speaker_0_files"} <= names
+    assert z["w1"].shape == (60, 512) and z["w1"].dtype == np.float32 and z["sample_rate"].dtype == np.int64
+    assert int(z["num_speakers"][0]) == 5 and int(z["sample_rate"][0]) == 44100 and int(z["bits"][0]) == 16
+    for k in range(5):
+        assert np.array_equal(z[f"w3_{k + 1}"], onet.w3[:, k]) and z[f"b3_{k + 1}"][0] == onet.b3[k]   # lib.rs:1091-1098
+    assert bytes(z["speaker_0_files"]).decode() == "a/x.wav\na/y.wav" and len(z["speaker_1_files"]) == 0
+    back = sz.SimpleNeuralNet.load(path, ctx=ctx)
+    assert all(np.array_equal(a, b) for a, b in zip(back.weights(), net.weights()))
+    assert back.file_lists()[0] == ["a/x.wav", "a/y.wav"] and back.file_lists()[3] == ["b/z.mp3"]
+    # numpy-written files: members get a ".npy" suffix; legacy dense w3/b3 (lib.rs:1199-1207)
+    p2 = str(tmp_path / "legacy.npz")
+    np.savez(p2, w1=onet.w1, b1=onet.b1, w2=onet.w2, b2=onet.b2, w3=onet.w3, b3=onet.b3, sample_rate=np.array([16000], np.int64),
+             bits=np.array([16], np.int64))
+    leg = sz.SimpleNeuralNet.load(p2, ctx=ctx)
+    assert leg.sample_rate == 16000 and all(np.array_equal(a, b) for a, b in zip(leg.weights(), onet.params()))
+    with pytest.raises(Exception):
+        sz.SimpleNeuralNet.load(str(tmp_path / "missing.npz"), ctx=ctx)
+
+
+def test_cached_features(sz, ctx, oracle, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    ex = sz.FeatureExtractor(ctx)
+    clip = oracle.synth_clip(1, 1, 0.5)
+    calls = []
+    def loader(p):
+        calls.append(p)
+        return clip
+    a = sz.load_cached_features("d/s.wav", loader, ex)
+    b = sz.load_cached_features("d/s.wav", loader, ex)
+    assert len(calls) == 1 and np.array_equal(a, b)
+    assert np.array_equal(np.load(tmp_path / "feature_cache" / "d_s.wav.npy"), a)     # lib.rs:550-579
+    assert len(sz.load_cached_features("short.wav", lambda p: clip[:100], ex)) == 0
+    assert not (tmp_path / "feature_cache" / "short.wav.npy").exists()                # empty sets are not written (lib.rs:573)
