@@ -29,6 +29,13 @@ __constant__ int c_mel_start[kMels];
 __constant__ int c_mel_len[kMels];
 __constant__ int c_mel_off[kMels];
 __constant__ float c_dct[kMfcc * kMels];  // unscaled DCT-II rows
+// The 26 filters hold 3..105 non-zero bins each; they are cut into chunks of <= 40 bins ("tasks") that are spread
+// over the 20 warps by size (longest-processing-time first) so the mel stage ends at the same time on every warp.
+struct MelTask { short k0, len, woff, slot; };
+constexpr int kMaxMelTasks = 48;
+__constant__ MelTask c_mel_tasks[kMaxMelTasks];      // grouped by warp
+__constant__ int c_mel_warp_begin[20 + 1];           // tasks of warp w: [begin[w], begin[w+1])
+__constant__ int c_mel_part_begin[kMels + 1];        // partial sums (slots) of filter m: [begin[m], begin[m+1])
 
 constexpr int kTile = 32;                 // frames per tile == lanes per warp
 constexpr int kWarps = 20;                // one warp per 20-point DFT column
@@ -41,7 +48,7 @@ constexpr int kRing = 64;                 // MFCC ring slots (power of two >= kT
 constexpr size_t kSmemPcm = size_t(kPcmRows) * kHopStride * 4;          // 26 532
 constexpr size_t kSmemS = size_t(kHalf) * kTile * 8;                    // 102 400
 constexpr size_t kSmemP = size_t(kBins) * kTile * 4;                    // 51 328
-constexpr size_t kSmemE = size_t(kMels) * kTile * 4;                    // 3 328
+constexpr size_t kSmemE = size_t(kMels + kMaxMelTasks) * kTile * 4;     // 9 472: ln energies + partial sums
 constexpr size_t kSmemRing = size_t(kMfcc) * kRing * 4;                 // 5 120
 constexpr size_t kSmemRed = size_t(kWarps) * 32 * 4;                    // 2 560
 constexpr size_t kSmemOut = size_t(kTile) * kFeat * 4;                  // 7 680
@@ -85,29 +92,50 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
         const uint32_t f_lo = sg.w_begin >= 2 ? sg.w_begin - 2 : 0;
         const uint32_t f_hi = min(sg.w_end + 2, n_total);
         const int16_t* clip = pcm + sg.pcm_off;
-        const bool aligned32 = (reinterpret_cast<uintptr_t>(clip) & 3) == 0;
         float* out_clip = out + sg.out_row * kFeat;
         uint32_t emit_next = sg.w_begin;
 
+        // PCM tile = hops [a, a + nf] = 33 * 800 B = 1650 uint4; thread t owns uint4 t, t + 640, t + 1280.
+        // They are fetched into registers one tile AHEAD (right after stage A has consumed the staging buffer), so the
+        // HBM latency hides behind stages B..7 of the previous tile.
+        constexpr int kVecPerHop = kHop / 8;                       // 50 uint4 per hop
+        constexpr int kVecPerTile = kPcmRows * kVecPerHop;         // 1650
+        constexpr int kPre = (kVecPerTile + kThreads - 1) / kThreads;  // 3
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(clip) & 15) == 0;
+        uint4 pre[kPre];
+        auto fetch_tile = [&](uint32_t ta) {
+            const uint32_t tnf = min(uint32_t(kTile), f_hi - ta);
+            const int16_t* src = clip + size_t(ta) * kHop;
+#pragma unroll
+            for (int r = 0; r < kPre; ++r) {
+                const int q = tid + r * kThreads;
+                pre[r] = make_uint4(0u, 0u, 0u, 0u);
+                if (q < int(tnf + 1) * kVecPerHop) {
+                    if (aligned16) {
+                        pre[r] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                    } else {
+                        const int16_t* s8 = src + size_t(q) * 8;
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            wv[e] = uint32_t(uint16_t(__ldg(s8 + 2 * e))) | (uint32_t(uint16_t(__ldg(s8 + 2 * e + 1))) << 16);
+                        pre[r] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+            }
+        };
+        fetch_tile(f_lo);
+
         for (uint32_t a = f_lo; a < f_hi; a += kTile) {
             const uint32_t nf = min(uint32_t(kTile), f_hi - a);
-            // ---- 1. stage hops [a, a + nf] as packed i16 pairs; rows past the tile are zero-filled -------------------
-            {
-                const int16_t* src = clip + size_t(a) * kHop;
-                const uint32_t nh = nf + 1;
-                for (int i = tid; i < kPcmRows * kHopWords; i += kThreads) {
-                    const int h = i / kHopWords, wd = i - h * kHopWords;
-                    uint32_t v = 0;
-                    if (uint32_t(h) < nh) {
-                        const size_t s = size_t(h) * kHop + size_t(wd) * 2;
-                        if (aligned32) {
-                            v = __ldg(reinterpret_cast<const uint32_t*>(src + s));
-                        } else {
-                            const uint32_t lo = uint16_t(__ldg(src + s)), hi = uint16_t(__ldg(src + s + 1));
-                            v = lo | (hi << 16);
-                        }
-                    }
-                    s_pcm[h * kHopStride + wd] = v;
+            // ---- 1. prefetched registers -> staging buffer (row stride 201 words keeps lane = frame conflict-free) ----
+#pragma unroll
+            for (int r = 0; r < kPre; ++r) {
+                const int q = tid + r * kThreads;
+                if (q < kVecPerTile) {
+                    const int h = q / kVecPerHop, c4 = q - h * kVecPerHop;
+                    uint32_t* d = s_pcm + h * kHopStride + c4 * 4;
+                    d[0] = pre[r].x; d[1] = pre[r].y; d[2] = pre[r].z; d[3] = pre[r].w;
                 }
             }
             __syncthreads();
@@ -127,13 +155,15 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 dft20(re, im);
                 float2* dst = s_S + n1 * kTile + lane;
                 dst[0] = make_float2(re[0], im[0]);
+                const float2* tw = c_tw400 + n1 * kR;
 #pragma unroll
                 for (int k2 = 1; k2 < kR; ++k2) {
-                    const float2 w = c_tw400[n1 * kR + k2];
+                    const float2 w = tw[k2];
                     dst[k2 * kR * kTile] = make_float2(fmaf(re[k2], w.x, -(im[k2] * w.y)), fmaf(re[k2], w.y, im[k2] * w.x));
                 }
             }
             __syncthreads();
+            if (a + kTile < f_hi) fetch_tile(a + kTile);   // staging buffer is free again: start the next tile's loads
 
             // ---- 3. stage B: warp = k2, lane = frame.  20-point DFT over n1, in place: row k2*20 + k1 = Z[k2 + 20 k1] --
             {
@@ -151,32 +181,68 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             }
             __syncthreads();
 
-            // ---- 4. real-input split + power: warp-uniform k, lane = frame -------------------------------------------
-            for (int k = warp; k <= 200; k += kWarps) {
-                if (k == 0) {
+            // ---- 4. real-input split + power.  warp = k2 handles bins k = k2 + 20 k1 (k <= 200) with their mirrors
+            //         400 - k = (20 - k2) + 20 (19 - k1): all row indices are affine in the unrolled k1 -----------------
+            {
+                const int k2 = warp;
+                if (k2 == 0) {
                     const float2 z = s_S[lane];
                     const float p0 = z.x + z.y, p1 = z.x - z.y;
                     s_P[lane] = 4.f * p0 * p0;
                     s_P[400 * kTile + lane] = 4.f * p1 * p1;
+#pragma unroll
+                    for (int k1 = 1; k1 <= 10; ++k1) {             // k = 20 k1, mirror row 20 - k1 (k1 = 10: itself)
+                        const float2 za = s_S[k1 * kTile + lane];
+                        const float2 zb = s_S[(kR - k1) * kTile + lane];
+                        const float2 w = c_tw800[kR * k1];
+                        float pk, pmk;
+                        split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
+                        s_P[(kR * k1) * kTile + lane] = pk;
+                        s_P[(kHalf - kR * k1) * kTile + lane] = pmk;
+                    }
                 } else {
-                    const float2 za = s_S[row_of_bin(k) * kTile + lane];
-                    const float2 zb = s_S[row_of_bin(kHalf - k) * kTile + lane];
-                    const float2 w = c_tw800[k];
-                    float pk, pmk;
-                    split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
-                    s_P[k * kTile + lane] = pk;
-                    s_P[(kHalf - k) * kTile + lane] = pmk;
+                    const float2* ra = s_S + (k2 * kR) * kTile + lane;
+                    const float2* rb = s_S + ((kR - k2) * kR + kR - 1) * kTile + lane;
+                    const float2* tw = c_tw800 + k2;
+                    float* pa = s_P + k2 * kTile + lane;
+                    float* pb = s_P + (kHalf - k2) * kTile + lane;
+#pragma unroll
+                    for (int k1 = 0; k1 < 10; ++k1) {
+                        const float2 za = ra[k1 * kTile];
+                        const float2 zb = rb[-k1 * kTile];
+                        const float2 w = tw[kR * k1];
+                        float pk, pmk;
+                        split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
+                        pa[(kR * k1) * kTile] = pk;
+                        pb[-(kR * k1) * kTile] = pmk;
+                    }
                 }
             }
             __syncthreads();
 
-            // ---- 5. mel + ln: warp-uniform filter, lane = frame (sparse rows of the 26 x 401 bank, lib.rs:303-310) -----
+            // ---- 5a. mel partial sums: size-balanced chunks of the sparse 26 x 401 bank (lib.rs:303-308) ----------------
+            for (int t = c_mel_warp_begin[warp]; t < c_mel_warp_begin[warp + 1]; ++t) {
+                const MelTask mt = c_mel_tasks[t];
+                const float* wv = c_melw + mt.woff;
+                const float* pp = s_P + mt.k0 * kTile + lane;
+                float acc0 = 0.f, acc1 = 0.f;
+                int i = 0;
+#pragma unroll 1
+                for (; i + 8 <= mt.len; i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        acc0 = fmaf(wv[i + u], pp[(i + u) * kTile], acc0);
+                        acc1 = fmaf(wv[i + u + 1], pp[(i + u + 1) * kTile], acc1);
+                    }
+                }
+                for (; i < mt.len; ++i) acc0 = fmaf(wv[i], pp[i * kTile], acc0);
+                s_E[(kMels + mt.slot) * kTile + lane] = acc0 + acc1;
+            }
+            __syncthreads();
+            // ---- 5b. ln(max(sum, 1e-12)) (lib.rs:309) --------------------------------------------------------------------
             for (int m = warp; m < kMels; m += kWarps) {
-                const int k0 = c_mel_start[m], len = c_mel_len[m];
-                const float* wv = c_melw + c_mel_off[m];
-                const float* pp = s_P + k0 * kTile + lane;
                 float acc = 0.f;
-                for (int i = 0; i < len; ++i) acc = fmaf(wv[i], pp[i * kTile], acc);
+                for (int q = c_mel_part_begin[m]; q < c_mel_part_begin[m + 1]; ++q) acc += s_E[(kMels + q) * kTile + lane];
                 s_E[m * kTile + lane] = logf(fmaxf(acc, 1e-12f));
             }
             __syncthreads();
@@ -184,10 +250,14 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             // ---- 6. DCT-II, first 20 coefficients: warp = coefficient, lane = frame (lib.rs:312-315) -------------------
             {
                 const int j = warp;
-                float acc = 0.f;
+                const float* dj = c_dct + j * kMels;
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-                for (int m = 0; m < kMels; ++m) acc = fmaf(c_dct[j * kMels + m], s_E[m * kTile + lane], acc);
-                if (uint32_t(lane) < nf) s_ring[j * kRing + ((a + lane) & (kRing - 1))] = acc;
+                for (int m = 0; m < kMels; m += 2) {
+                    acc0 = fmaf(dj[m], s_E[m * kTile + lane], acc0);
+                    acc1 = fmaf(dj[m + 1], s_E[(m + 1) * kTile + lane], acc1);
+                }
+                if (uint32_t(lane) < nf) s_ring[j * kRing + ((a + lane) & (kRing - 1))] = acc0 + acc1;
             }
             __syncthreads();
 
@@ -307,6 +377,43 @@ szb_status upload_frontend_tables() {
     SZB_CUDA(cudaMemcpyToSymbol(c_mel_len, csr.len, sizeof(csr.len)));
     SZB_CUDA(cudaMemcpyToSymbol(c_mel_off, csr.off, sizeof(int) * kMels));
     SZB_CUDA(cudaMemcpyToSymbol(c_dct, dct.data(), dct.size() * sizeof(float)));
+    {   // mel tasks: chunks of <= 40 bins, longest-processing-time-first over the warps
+        struct T { MelTask t; int m; };
+        std::vector<T> tasks;
+        int part_begin[kMels + 1];
+        int slot = 0;
+        for (int m = 0; m < kMels; ++m) {
+            part_begin[m] = slot;
+            const int len = csr.len[m], parts = std::max(1, (len + 39) / 40);
+            for (int p = 0; p < parts; ++p) {
+                const int b = len * p / parts, e = len * (p + 1) / parts;
+                MelTask t;
+                t.k0 = short(csr.start[m] + b); t.len = short(e - b); t.woff = short(csr.off[m] + b); t.slot = short(slot++);
+                tasks.push_back({ t, m });
+            }
+        }
+        part_begin[kMels] = slot;
+        SZB_REQUIRE(slot <= kMaxMelTasks, "mel task table overflow (%d)", slot);
+        std::sort(tasks.begin(), tasks.end(), [](const T& x, const T& y) { return x.t.len > y.t.len; });
+        std::vector<std::vector<MelTask>> per_warp(kWarps);
+        std::vector<int> load(kWarps, 0);
+        for (const T& t : tasks) {
+            const int w = int(std::min_element(load.begin(), load.end()) - load.begin());
+            per_warp[w].push_back(t.t);
+            load[w] += t.t.len + 6;   // + fixed per-task overhead
+        }
+        MelTask flat[kMaxMelTasks] = {};
+        int warp_begin[kWarps + 1];
+        int n = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            warp_begin[w] = n;
+            for (const MelTask& t : per_warp[w]) flat[n++] = t;
+        }
+        warp_begin[kWarps] = n;
+        SZB_CUDA(cudaMemcpyToSymbol(c_mel_tasks, flat, sizeof flat));
+        SZB_CUDA(cudaMemcpyToSymbol(c_mel_warp_begin, warp_begin, sizeof warp_begin));
+        SZB_CUDA(cudaMemcpyToSymbol(c_mel_part_begin, part_begin, sizeof part_begin));
+    }
     SZB_CUDA(cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
     return SZB_OK;
 }
