@@ -153,6 +153,7 @@ void szb_ctx_destroy(szb_ctx* ctx) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
     }
+    for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
                        &ctx->x })
         b->release();
@@ -338,44 +339,121 @@ szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in,
     return SZB_OK;
 }
 
-szb_status szb_extract_batch_dev(szb_ctx* ctx, const int16_t* d_pcm, const uint64_t* clip_off, uint32_t n_clips,
-                                 uint32_t rate, float* d_feats, uint64_t cap_windows, uint64_t* win_off) {
-    SZB_REQUIRE(ctx && clip_off && win_off, "szb_extract_batch_dev: NULL argument");
-    SZB_REQUIRE(rate > 0, "szb_extract_batch_dev: rate is 0");
+// Shared driver of the two batch entry points.  With `h_pcm` / `h_feats` set (host entry point) the batch is cut into
+// chunks of clips that flow through a three-stage pipeline -- H2D copy (copy_in stream), resample + extract (the
+// context's stream), D2H copy (copy_out stream) -- so the PCIe transfers of neighbouring chunks overlap the kernels.
+static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const int16_t* h_pcm, const uint64_t* clip_off,
+                                     uint32_t n_clips, uint32_t rate, float* d_feats, float* h_feats, uint64_t cap_windows,
+                                     uint64_t* win_off) {
     for (uint32_t c = 0; c < n_clips; ++c)
-        SZB_REQUIRE(clip_off[c + 1] >= clip_off[c], "szb_extract_batch_dev: clip_off not monotone at %u", c);
+        SZB_REQUIRE(clip_off[c + 1] >= clip_off[c], "extract_batch: clip_off not monotone at %u", c);
     SZB_CUDA(cudaSetDevice(ctx->device));
     std::vector<uint64_t> off44, woff;
     batch_layout(clip_off, n_clips, rate, off44, woff);
     std::memcpy(win_off, woff.data(), woff.size() * sizeof(uint64_t));
     const uint64_t total = woff[n_clips];
-    SZB_REQUIRE(cap_windows >= total, "szb_extract_batch_dev: capacity %llu windows < %llu", (unsigned long long)cap_windows,
+    SZB_REQUIRE(cap_windows >= total, "extract_batch: capacity %llu windows < %llu", (unsigned long long)cap_windows,
                 (unsigned long long)total);
     if (total == 0) return SZB_OK;
-    SZB_REQUIRE(d_pcm && d_feats, "szb_extract_batch_dev: NULL device pointer");
-    const int16_t* d_pcm44 = d_pcm + clip_off[0];
-    if (rate != SZB_SAMPLE_RATE) {
-        // unfused path: resample every clip into a 44.1 kHz scratch buffer, then extract from it
+    SZB_REQUIRE(d_pcm && d_feats, "extract_batch: NULL buffer");
+    const bool resample = rate != SZB_SAMPLE_RATE;
+    const bool piped = h_pcm != nullptr;
+    const uint64_t first = clip_off[0];
+
+    // chunking: one chunk for the device-resident call, ~48 MB of traffic per chunk for the host call
+    std::vector<uint32_t> chunk_begin{ 0 };
+    if (piped) {
+        const uint64_t target = 48ull << 20;
+        uint64_t acc = 0;
+        for (uint32_t c = 0; c < n_clips; ++c) {
+            acc += (clip_off[c + 1] - clip_off[c]) * 2 + (woff[c + 1] - woff[c]) * SZB_FEATURE_SIZE * 4;
+            if (acc >= target && c + 1 < n_clips) {
+                chunk_begin.push_back(c + 1);
+                acc = 0;
+            }
+        }
+    }
+    chunk_begin.push_back(n_clips);
+    const size_t n_chunks = chunk_begin.size() - 1;
+
+    const int16_t* d_pcm44 = d_pcm;   // device layout: clip c starts at d_pcm[clip_off[c] - first] (rate 44.1k) ...
+    uint64_t* d_in_off = nullptr;
+    uint64_t* d_out_off = nullptr;
+    if (resample) {                   // ... or at misc[off44[c]] after the resampler
         SZB_TRY(ctx->misc.reserve(off44[n_clips] * 2 + 64));
         SZB_TRY(ctx->labels.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
         SZB_TRY(ctx->h_misc.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
         uint64_t* h = ctx->h_misc.as<uint64_t>();
-        std::memcpy(h, clip_off, (size_t(n_clips) + 1) * sizeof(uint64_t));
-        uint64_t* h_out = h + n_clips + 1;
-        uint64_t max_out = 0;
-        for (uint32_t c = 0; c <= n_clips; ++c) h_out[c] = off44[c];
-        for (uint32_t c = 0; c < n_clips; ++c)
-            max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
-        SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, h, (size_t(n_clips) + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                                 ctx->stream));
-        SZB_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, off44[n_clips] * 2 + 64, ctx->stream));
-        SZB_TRY(launch_resample(ctx, d_pcm, ctx->labels.as<uint64_t>(), ctx->labels.as<uint64_t>() + n_clips + 1, n_clips,
-                                max_out, rate, ctx->misc.as<int16_t>()));
+        for (uint32_t c = 0; c <= n_clips; ++c) {
+            h[c] = clip_off[c] - first;
+            h[n_clips + 1 + c] = off44[c];
+        }
+        SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, h, (size_t(n_clips) + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_in_off = ctx->labels.as<uint64_t>();
+        d_out_off = d_in_off + n_clips + 1;
         d_pcm44 = ctx->misc.as<int16_t>();
     }
+    // segment table of every chunk, uploaded once
     std::vector<Segment> segs;
-    build_segments(off44.data(), woff.data(), n_clips, ctx->sm_count, segs);
-    return launch_extract(ctx, d_pcm44, segs, d_feats);
+    std::vector<size_t> seg_begin(n_chunks + 1, 0);
+    std::vector<uint64_t> seg_off(size_t(n_clips) + 1);
+    for (uint32_t c = 0; c <= n_clips; ++c) seg_off[c] = resample ? off44[c] : clip_off[c] - first;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        seg_begin[k] = segs.size();
+        build_segments(seg_off.data(), woff.data(), chunk_begin[k], chunk_begin[k + 1], ctx->sm_count, segs);
+    }
+    seg_begin[n_chunks] = segs.size();
+    SZB_TRY(upload_segments(ctx, segs, uint32_t(n_chunks)));
+
+    if (piped) {
+        while (ctx->pipe_events.size() < 2 * n_chunks + 1) {
+            cudaEvent_t e;
+            SZB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->pipe_events.push_back(e);
+        }
+        // the copy streams must not start before the uploads above (and any earlier work on the stream) are done
+        SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * n_chunks], ctx->stream));
+        SZB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->pipe_events[2 * n_chunks], 0));
+        SZB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_events[2 * n_chunks], 0));
+    }
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const uint32_t c0 = chunk_begin[k], c1 = chunk_begin[k + 1];
+        if (piped) {
+            const uint64_t s0 = clip_off[c0] - first, s1 = clip_off[c1] - first;
+            if (s1 > s0)
+                SZB_CUDA(cudaMemcpyAsync(const_cast<int16_t*>(d_pcm) + s0, h_pcm + clip_off[c0], (s1 - s0) * 2, cudaMemcpyHostToDevice,
+                                         ctx->copy_in));
+            SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k], ctx->copy_in));
+            SZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
+        }
+        if (resample) {
+            uint64_t max_out = 0;
+            for (uint32_t c = c0; c < c1; ++c) max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
+            SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
+        }
+        SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats));
+        if (piped) {
+            SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
+            SZB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_events[2 * k + 1], 0));
+            const uint64_t w0 = woff[c0], w1 = woff[c1];
+            if (w1 > w0)
+                SZB_CUDA(cudaMemcpyAsync(h_feats + w0 * SZB_FEATURE_SIZE, d_feats + w0 * SZB_FEATURE_SIZE,
+                                         (w1 - w0) * SZB_FEATURE_SIZE * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+    }
+    if (piped) {
+        SZB_CUDA(cudaStreamSynchronize(ctx->copy_out));
+        SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SZB_OK;
+}
+
+szb_status szb_extract_batch_dev(szb_ctx* ctx, const int16_t* d_pcm, const uint64_t* clip_off, uint32_t n_clips,
+                                 uint32_t rate, float* d_feats, uint64_t cap_windows, uint64_t* win_off) {
+    SZB_REQUIRE(ctx && clip_off && win_off, "szb_extract_batch_dev: NULL argument");
+    SZB_REQUIRE(rate > 0, "szb_extract_batch_dev: rate is 0");
+    return extract_batch_impl(ctx, d_pcm ? d_pcm + clip_off[0] : nullptr, nullptr, clip_off, n_clips, rate, d_feats, nullptr,
+                              cap_windows, win_off);
 }
 
 szb_status szb_extract_batch(szb_ctx* ctx, const int16_t* pcm, const uint64_t* clip_off, uint32_t n_clips, uint32_t rate,
@@ -396,15 +474,8 @@ szb_status szb_extract_batch(szb_ctx* ctx, const int16_t* pcm, const uint64_t* c
     SZB_CUDA(cudaSetDevice(ctx->device));
     SZB_TRY(ctx->pcm.reserve(n_samples * 2 + 64));
     SZB_TRY(ctx->feats.reserve(total * SZB_FEATURE_SIZE * sizeof(float)));
-    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, pcm + first, n_samples * 2, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<uint64_t> rel(size_t(n_clips) + 1);
-    for (uint32_t c = 0; c <= n_clips; ++c) rel[c] = clip_off[c] - first;
-    SZB_TRY(szb_extract_batch_dev(ctx, ctx->pcm.as<int16_t>(), rel.data(), n_clips, rate, ctx->feats.as<float>(), total,
-                                  win_off));
-    SZB_CUDA(cudaMemcpyAsync(feats, ctx->feats.ptr, total * SZB_FEATURE_SIZE * sizeof(float), cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return SZB_OK;
+    return extract_batch_impl(ctx, ctx->pcm.as<int16_t>(), pcm, clip_off, n_clips, rate, ctx->feats.as<float>(), feats, cap_windows,
+                              win_off);
 }
 
 szb_status szb_extract(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, float* feats, uint64_t cap_windows,

@@ -69,6 +69,7 @@ struct szb_ctx {
     double ktime_ms = 0.0;
     uint64_t ktime_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime_pending;
+    std::vector<cudaEvent_t> pipe_events;                // chunk pipeline of szb_extract_batch
     // scratch
     szb::DevBuf segs, counter, pcm, feats, taps, labels, misc, probs, x;
     szb::PinnedBuf h_segs, h_misc;

@@ -311,37 +311,112 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
     }
 }
 
-// ---- standalone resampler (resample_to_44100, lib.rs:186-209; polyphase spec in DESIGN.md) ---------------------------
-// One thread per output sample; taps [L][16] in global memory (L1/L2 resident).  Bit-exact contract:
-// acc = fma(c[p][t], float(x[i]), acc), t = 0..15, then clamp and truncate toward zero.
-__global__ void resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_off,
-                                const uint64_t* __restrict__ out_off, uint32_t n_clips, const float* __restrict__ taps,
-                                uint32_t L, uint32_t M, uint32_t rate, int16_t* __restrict__ out) {
-    const uint32_t c = blockIdx.y;
-    if (c >= n_clips) return;
-    const uint64_t n_in = in_off[c + 1] - in_off[c];
-    const uint64_t n_out = n_in * 44100ull / rate;  // lib.rs:196 (out_off may be padded past this)
-    const int16_t* x = in + in_off[c];
-    int16_t* y = out + out_off[c];
-    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n_out; j += uint64_t(gridDim.x) * blockDim.x) {
-        const uint64_t pos = j * M;
-        const int64_t i0 = int64_t(pos / L);
-        const uint32_t p = uint32_t(pos - uint64_t(i0) * L);
-        const float4* cp = reinterpret_cast<const float4*>(taps + size_t(p) * kResTaps);
-        float acc = 0.f;
+// ---- resampler (resample_to_44100, lib.rs:186-209; polyphase spec in DESIGN.md "Resampler") --------------------------
+// Bit-exact contract: acc = fma(c[p][t], float(x[i0 - 7 + t]), acc) for t = 0..15 in float32 (inputs outside the clip
+// are 0), then clamp to [-32768, 32767] and truncate toward zero (lib.rs:205-208).
+//
+// Mapping: outputs are walked in rows of Lb samples (Lb a multiple of lcm(L, 3)); a block works on tiles of kResRows
+// rows.  The tile's input span is loaded once (coalesced), converted to float once and staged in shared memory; the
+// tile's output is staged in shared memory as i16 and leaves with 16-byte coalesced stores -- every input sample is
+// read from HBM once and every output sample written once.  A thread owns THREE adjacent output columns for the whole
+// kernel, so their phases and taps never change and live in registers, and the input index advances by the exact
+// integer Lb M / L per row -- no division or table lookup in the loop.  The three outputs read overlapping input
+// windows: one window of 16 + D samples is fetched from shared memory, and each output applies its 16 taps shifted by
+// its own offset d_k <= D inside that window (the padding taps are exact zeros, so the accumulation order and the
+// result bits are unchanged): 5.7 shared loads and 17 FMAs per output instead of 16 + 16.
+constexpr int kResRows = 32;
+
+template <int D>
+__global__ void __launch_bounds__(160, 4)
+resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ out_off,
+                uint32_t n_clips, const float* __restrict__ taps, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G, uint32_t rate,
+                int16_t* __restrict__ out) {
+    constexpr int W = kResTaps + D;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const uint32_t in_per_row = uint32_t(uint64_t(Lb) * M / L);   // exact: L divides Lb
+    const uint32_t n_in_tile = kResRows * in_per_row + W;         // staged input samples per tile
+    float* s_in = reinterpret_cast<float*>(rs_smem);
+    int16_t* s_out = reinterpret_cast<int16_t*>(rs_smem + ((size_t(n_in_tile) * 4 + 15) & ~size_t(15)));
+    const uint32_t tid = threadIdx.x, g = tid;
+    const bool worker = g < G;
+    uint32_t q0 = 0;
+    float c[3][W];
+    if (worker) {
+        q0 = uint32_t((uint64_t(3 * g) * M) / L);
 #pragma unroll
-        for (int q = 0; q < kResTaps / 4; ++q) {
-            const float4 cv = __ldg(cp + q);
-            const float cs[4] = { cv.x, cv.y, cv.z, cv.w };
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t pos = uint64_t(3 * g + k) * M;
+            const uint32_t p = uint32_t(pos % L), d = uint32_t(pos / L) - q0;
+            const float* cp = taps + size_t(p) * kResTaps;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t i = i0 - (kResTaps / 2 - 1) + q * 4 + r;
-                const float xv = (i >= 0 && uint64_t(i) < n_in) ? float(x[i]) : 0.f;
-                acc = fmaf(cs[r], xv, acc);
+            for (int t = 0; t < W; ++t) {
+                const int src = t - int(d);
+                c[k][t] = (src >= 0 && src < kResTaps) ? __ldg(cp + src) : 0.f;
             }
         }
-        acc = fminf(fmaxf(acc, -32768.f), 32767.f);
-        y[j] = int16_t(__float2int_rz(acc));
+    }
+    for (uint32_t clip = blockIdx.y; clip < n_clips; clip += gridDim.y) {
+        const int64_t n_in = int64_t(in_off[clip + 1] - in_off[clip]);
+        const uint64_t n_out = uint64_t(n_in) * 44100ull / rate;   // lib.rs:196 (out_off may be padded past this)
+        const int16_t* x = in + in_off[clip];
+        int16_t* y = out + out_off[clip];
+        const uint64_t n_rows = (n_out + Lb - 1) / Lb;
+        for (uint64_t row0 = uint64_t(blockIdx.x) * kResRows; row0 < n_rows; row0 += uint64_t(gridDim.x) * kResRows) {
+            // ---- stage the tile's input span as float (zeros outside the clip) ----
+            const int64_t i_lo = int64_t(row0) * in_per_row - (kResTaps / 2 - 1);
+            for (uint32_t base = tid; base < n_in_tile; base += 8 * blockDim.x) {
+                int16_t v[8];                                      // 8 independent loads in flight per thread
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t i = base + u * blockDim.x;
+                    const int64_t gi = i_lo + i;
+                    v[u] = (i < n_in_tile && gi >= 0 && gi < n_in) ? __ldg(x + gi) : int16_t(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t i = base + u * blockDim.x;
+                    if (i < n_in_tile) s_in[i] = float(v[u]);
+                }
+            }
+            // outputs of the tile: [j_lo, j_hi); staged at s_out[shift + (j - j_lo)] so that global and shared addresses
+            // are congruent modulo 16 bytes
+            const uint64_t j_lo = row0 * Lb, j_hi = min(n_out, j_lo + uint64_t(kResRows) * Lb);
+            const uint32_t shift = uint32_t((reinterpret_cast<uintptr_t>(y + j_lo) >> 1) & 7);
+            __syncthreads();
+            if (worker) {
+                const uint32_t rows_here = uint32_t((j_hi - j_lo + Lb - 1) / Lb);
+                for (uint32_t r = 0; r < rows_here; ++r) {
+                    const float* wv = s_in + r * in_per_row + q0;
+                    float w[W];
+#pragma unroll
+                    for (int t = 0; t < W; ++t) w[t] = wv[t];
+                    float acc[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+                    for (int t = 0; t < W; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) acc[k] = fmaf(c[k][t], w[t], acc[k]);
+                    }
+                    int16_t* so = s_out + shift + r * Lb + 3 * g;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) so[k] = int16_t(__float2int_rz(fminf(fmaxf(acc[k], -32768.f), 32767.f)));
+                }
+            }
+            __syncthreads();
+            // ---- coalesced write-out: scalar head up to the first 16-byte boundary, uint4 body, scalar tail ----
+            {
+                const uint32_t n = uint32_t(j_hi - j_lo);
+                int16_t* dst = y + j_lo;
+                const uint32_t head = min(n, (8u - shift) & 7u);
+                const uint32_t body = (n - head) / 8;
+                if (tid < head) dst[tid] = s_out[shift + tid];
+                const uint4* sv = reinterpret_cast<const uint4*>(s_out + shift + head);
+                uint4* dv = reinterpret_cast<uint4*>(dst + head);
+                for (uint32_t i = tid; i < body; i += blockDim.x) dv[i] = sv[i];
+                const uint32_t tail0 = head + body * 8;
+                if (tid < n - tail0) dst[tail0 + tid] = s_out[shift + tail0 + tid];
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -420,14 +495,13 @@ szb_status upload_frontend_tables() {
 
 // Split clips into (clip, window-range) segments: whole clips when there is enough work to fill the machine, else
 // ranges of >= 64 windows so short batches still spread over the SMs.
-void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_t n_clips, int sm_count,
+void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_t clip_begin, uint32_t clip_end, int sm_count,
                     std::vector<Segment>& segs) {
-    segs.clear();
-    const uint64_t total = win_off[n_clips];
+    const uint64_t total = win_off[clip_end] - win_off[clip_begin];
     uint64_t target = total / (uint64_t(sm_count) * 4);
     target = std::max<uint64_t>(64, std::min<uint64_t>(target, 4096));
     target = (target + kTile - 1) / kTile * kTile;
-    for (uint32_t c = 0; c < n_clips; ++c) {
+    for (uint32_t c = clip_begin; c < clip_end; ++c) {
         const uint64_t n = win_off[c + 1] - win_off[c];
         if (n == 0) continue;
         const uint64_t parts = (n + target + target / 2 - 1) / (target + target / 2);  // allow 1.5x target per segment
@@ -444,24 +518,32 @@ void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_
     }
 }
 
-szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, const std::vector<Segment>& segs, float* d_feats) {
-    if (segs.empty()) return SZB_OK;
-    SZB_TRY(ctx->segs.reserve(segs.size() * sizeof(Segment)));
-    SZB_TRY(ctx->counter.reserve(sizeof(unsigned int)));
-    SZB_TRY(ctx->h_segs.reserve(segs.size() * sizeof(Segment)));
-    std::memcpy(ctx->h_segs.ptr, segs.data(), segs.size() * sizeof(Segment));
-    SZB_CUDA(cudaMemcpyAsync(ctx->segs.ptr, ctx->h_segs.ptr, segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    SZB_CUDA(cudaMemsetAsync(ctx->counter.ptr, 0, sizeof(unsigned int), ctx->stream));
-    const int grid = int(std::min<size_t>(segs.size(), size_t(ctx->sm_count)));
+// Uploads a segment table (and zeroes `n_queues` work-queue counters) for one or more extract launches.
+szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint32_t n_queues) {
+    SZB_TRY(ctx->segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(Segment)));
+    SZB_TRY(ctx->counter.reserve(std::max<uint32_t>(1, n_queues) * sizeof(unsigned int)));
+    SZB_TRY(ctx->h_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(Segment)));
+    if (!segs.empty()) {
+        std::memcpy(ctx->h_segs.ptr, segs.data(), segs.size() * sizeof(Segment));
+        SZB_CUDA(cudaMemcpyAsync(ctx->segs.ptr, ctx->h_segs.ptr, segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    }
+    SZB_CUDA(cudaMemsetAsync(ctx->counter.ptr, 0, std::max<uint32_t>(1, n_queues) * sizeof(unsigned int), ctx->stream));
+    return SZB_OK;
+}
+
+// Launches the extraction kernel over segments [seg_begin, seg_begin + n_segs) of the uploaded table, queue `queue`.
+szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats) {
+    if (n_segs == 0) return SZB_OK;
+    const int grid = int(std::min<size_t>(n_segs, size_t(ctx->sm_count)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->ktime_on) {
         SZB_CUDA(cudaEventCreate(&e0));
         SZB_CUDA(cudaEventCreate(&e1));
         SZB_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    extract_kernel<<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>(), uint32_t(segs.size()),
-                                                               ctx->counter.as<unsigned int>(), d_feats);
+    extract_kernel<<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
+                                                               ctx->counter.as<unsigned int>() + queue, d_feats);
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (ctx->ktime_on) {
@@ -471,11 +553,25 @@ szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, const std::vecto
     return SZB_OK;
 }
 
+template <int D>
+static szb_status launch_resample_t(szb_ctx* ctx, dim3 grid, uint32_t threads, size_t smem, const int16_t* d_in, const uint64_t* d_in_off,
+                                    const uint64_t* d_out_off, uint32_t n_clips, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G,
+                                    uint32_t rate, int16_t* d_out) {
+    SZB_CUDA(cudaFuncSetAttribute(resample_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    resample_kernel<D><<<grid, threads, smem, ctx->stream>>>(d_in, d_in_off, d_out_off, n_clips, ctx->taps.as<float>(), L, M, Lb, G,
+                                                              rate, d_out);
+    SZB_CUDA(cudaGetLastError());
+    return SZB_OK;
+}
+
 szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
                            uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
     if (n_clips == 0 || max_out == 0) return SZB_OK;
     uint32_t L, M;
     resample_ratio(rate, L, M);
+    // three adjacent outputs span at most ceil(2 M / L) input samples
+    const uint32_t span = uint32_t((2ull * M + L - 1) / L);
+    SZB_REQUIRE(span <= 5 && L <= 4096, "resample: unsupported rate %u (L = %u, M = %u)", rate, L, M);
     if (ctx->taps_rate != rate) {
         const auto taps = resample_taps(rate);
         SZB_TRY(ctx->taps.reserve(taps.size() * sizeof(float)));
@@ -483,16 +579,24 @@ szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_
         SZB_CUDA(cudaStreamSynchronize(ctx->stream));  // taps is a temporary
         ctx->taps_rate = rate;
     }
-    const int threads = 256;
-    const uint64_t bx = std::min<uint64_t>((max_out + threads - 1) / threads, 4096);
-    for (uint32_t c0 = 0; c0 < n_clips; c0 += 65535) {
-        const uint32_t nc = std::min<uint32_t>(65535, n_clips - c0);
-        dim3 grid(uint32_t(bx), nc);
-        resample_kernel<<<grid, threads, 0, ctx->stream>>>(d_in, d_in_off + c0, d_out_off + c0, nc, ctx->taps.as<float>(), L,
-                                                           M, rate, d_out);
-        SZB_CUDA(cudaGetLastError());
-        ctx->launches += 1;
-    }
+    const uint32_t Lp = L % 3 == 0 ? L : 3 * L;             // lcm(L, 3)
+    const uint32_t mult = std::max<uint32_t>(1, 3 * 128 / Lp);
+    const uint32_t Lb = Lp * mult, G = Lb / 3;              // G threads cover one row of Lb outputs
+    SZB_REQUIRE(G <= 160, "resample: rate %u needs %u threads per row", rate, G);
+    const uint32_t threads = (G + 31) / 32 * 32;
+    const uint32_t D = span <= 1 ? 1 : (span <= 3 ? 3 : 5);
+    const uint64_t in_per_row = uint64_t(Lb) * M / L;
+    const size_t smem = ((size_t(kResRows) * in_per_row + kResTaps + D) * 4 + 15) / 16 * 16 + (size_t(kResRows) * Lb + 16) * 2;
+    SZB_REQUIRE(smem <= 200 * 1024, "resample: rate %u needs %zu bytes of shared memory", rate, smem);
+    const uint64_t tiles = ((max_out + Lb - 1) / Lb + kResRows - 1) / kResRows;
+    const uint32_t gy = std::min<uint32_t>(n_clips, 65535);
+    const uint64_t want_x = std::max<uint64_t>(1, (uint64_t(ctx->sm_count) * 16 + gy - 1) / gy);
+    const uint32_t gx = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(want_x, tiles)));
+    dim3 grid(gx, gy);
+    if (D == 1) SZB_TRY(launch_resample_t<1>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
+    else if (D == 3) SZB_TRY(launch_resample_t<3>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
+    else SZB_TRY(launch_resample_t<5>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
+    ctx->launches += 1;
     return SZB_OK;
 }
 
