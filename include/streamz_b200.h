@@ -133,6 +133,11 @@ uint32_t szb_net_output_size(const szb_net* net);
 /* add_output_class (lib.rs:797-821): w3 gains a column (given, or U(-0.5,0.5) from `seed` when NULL), b3 a zero. */
 szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t seed);
 void szb_net_destroy(szb_net* net);
+/* Arithmetic of the dense layers.  1 (default): tensor cores, tcgen05 kind::tf32 with the 3xTF32 split
+ * (x = hi + lo; A_lo B_hi + A_hi B_lo + A_hi B_hi), FP32-equivalent for parity with the reference's FP32 `dot`.
+ * 2: plain TF32 tensor cores (10-bit mantissa inputs, FP32 accumulate).  0: FP32 CUDA-core GEMM. */
+szb_status szb_net_set_precision(szb_net* net, int32_t mode);
+int32_t szb_net_get_precision(const szb_net* net);
 /* record_training_file / file_lists (lib.rs:855-867): host-side bookkeeping saved into model.npz as
  * speaker_<i>_files.  szb_net_file_list returns the newline-joined list of `speaker` (len excludes the NUL). */
 szb_status szb_net_record_training_file(szb_net* net, uint32_t speaker, const char* path);

@@ -72,6 +72,8 @@ SIGNATURES = {
     "szb_net_output_size": (u32, [vp]),
     "szb_net_add_output_class": (i32, [vp, vp, u64]),
     "szb_net_destroy": (None, [vp]),
+    "szb_net_set_precision": (i32, [vp, i32]),
+    "szb_net_get_precision": (i32, [vp]),
     "szb_net_record_training_file": (i32, [vp, u32, C.c_char_p]),
     "szb_net_file_list": (i32, [vp, u32, vp, sz, P(sz)]),
     "szb_net_forward": (i32, [vp, vp, u64, vp]),

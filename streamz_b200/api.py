@@ -260,6 +260,13 @@ class SimpleNeuralNet:
     def output_size(self) -> int:
         return int(N.lib.szb_net_output_size(self._h))
 
+    PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+
+    def set_precision(self, mode) -> "SimpleNeuralNet":
+        """'3xtf32' (default, tensor cores, FP32-equivalent), 'tf32' (tensor cores, fastest) or 'fp32' (CUDA cores)."""
+        N.check(N.lib.szb_net_set_precision(self._h, self.PRECISIONS.get(mode, mode)))
+        return self
+
     def weights(self):
         i, h1, h2, c = self.dims
         w1, b1 = np.empty((i, h1), np.float32), np.empty(h1, np.float32)

@@ -1,0 +1,301 @@
+// Tensor-core GEMM for the SimpleNeuralNet layers (streamz-rs/src/lib.rs:880-891, 1013-1045) on sm_100a:
+// tcgen05.mma (kind::tf32) with the accumulator in TMEM, operands staged in shared memory in the canonical
+// K-major SWIZZLE_128B layout, completion tracked with tcgen05.commit -> mbarrier, epilogue via tcgen05.ld.
+//
+//   C[M, N] (+)= A[M, K] * B[N, K]^T          A and B are FP32, K contiguous ("TN": both operands K-major)
+//
+// Every GEMM of the forward and backward pass is brought into this one form by keeping transposed copies of the
+// weights and by letting the producing epilogue also write the transposed activation (see mlp.cu), so a single,
+// well-tested operand layout serves all eight products of a training step.
+//
+// Precision: PASSES = 1 is plain TF32 (10-bit mantissa inputs, FP32 accumulate).  PASSES = 3 is the split
+// "3xTF32" scheme: x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and C += A_lo B_hi + A_hi B_lo + A_hi B_hi,
+// which restores ~FP32 accuracy (error ~2^-21 relative per product) for parity with the reference's FP32 arithmetic.
+#pragma once
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace szb {
+namespace tc {
+
+constexpr int BM = 128;        // UMMA M (one CTA, cta_group::1)
+constexpr int BK = 32;         // K per stage: 32 floats = 128 bytes = one SWIZZLE_128B row
+constexpr int UK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
+constexpr int kStages = 2;
+constexpr int kThreadsTc = 128;
+
+enum EpiTc : int { TC_BIAS = 0, TC_BIAS_RELU = 1, TC_BIAS_TANH = 2, TC_MUL_DTANH = 3, TC_MUL_DRELU = 4, TC_ATOMIC = 5 };
+
+struct GemmArgs {
+    const float* A; int lda;      // [M][lda]
+    const float* B; int ldb;      // [N][ldb]
+    float* C; int ldc;            // [M][ldc] (may be null when only CT is wanted)
+    float* CT; int ldct;          // optional transposed output [N][ldct]
+    const float* bias;            // [N]   (TC_BIAS*)
+    const float* aux; int ldaux;  // [M][ldaux] (TC_MUL_*)
+    int M, N, K;
+    int k_chunk;                  // K range per blockIdx.z (multiple of BK); == K rounded up when no split
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();   // never hang the GPU on a protocol bug
+    }
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes, groups of 8
+// rows 1024 bytes apart (SBO = 64 x 16 B), LBO = 1 (ignored for swizzled K-major), version 1 (Blackwell), layout 2.
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t(64) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (2), both K-major, N >> 3, M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a [rows][128 B] SWIZZLE_128B tile (1024-B aligned).
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4); }
+
+// Nearest TF32 value (10-bit mantissa, round half up in magnitude): x - tf32_hi(x) is then exact in FP32 and at most
+// 2^-11 |x|, so the three-product split carries ~2^-21 relative error per term.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u); }
+
+template <int BN, int PASSES>
+struct SmemLayout {
+    static constexpr int kATile = BM * BK * 4;                 // 16 KB
+    static constexpr int kBTile = BN * BK * 4;
+    static constexpr int kParts = PASSES == 3 ? 2 : 1;         // hi (+ lo)
+    static constexpr int kStageBytes = kParts * (kATile + kBTile);
+    static constexpr int kTotal = kStages * kStageBytes + 1024;  // + alignment slack
+};
+
+// One CTA = one 128 x BN tile of C (x one K split).  128 threads: all of them stage operands; one issues the MMAs;
+// in the epilogue thread t owns accumulator row t (TMEM lane t).
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
+    static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+    using SL = SmemLayout<BN, PASSES>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    __shared__ uint64_t s_bar[kStages];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
+    const int n_kb = (kb1 - kb0 + BK - 1) / BK;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem;
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+
+    const bool a_vec = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    const bool b_vec = (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+
+    // A [rows][32]-float K-slab is 8 sixteen-byte chunks per row.  Thread t owns chunk (t & 7) of rows (t >> 3) + 16 u:
+    // 8 consecutive threads read one 128-byte row segment.  The slab of k-block kb + 1 is fetched into registers while
+    // the tensor core works on k-block kb, so global/L2 latency is paid once per tile, not once per k-block.
+    constexpr int kRa = BM * 8 / kThreadsTc, kRb = BN * 8 / kThreadsTc;
+    const int lr = tid >> 3, lc = tid & 7;
+    auto gload = [&](const float* src, int ld, int row0, int rows_end, int k0, int kend, bool vec, int u) -> float4 {
+        const int gr = row0 + lr + 16 * u, gk = k0 + lc * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < rows_end && gk < kend) {
+            const float* p = src + size_t(gr) * ld + gk;
+            if (vec && gk + 4 <= kend) {
+                v = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+                v.x = __ldg(p);
+                if (gk + 1 < kend) v.y = __ldg(p + 1);
+                if (gk + 2 < kend) v.z = __ldg(p + 2);
+                if (gk + 3 < kend) v.w = __ldg(p + 3);
+            }
+        }
+        return v;
+    };
+    auto sstore = [&](unsigned char* hi, unsigned char* lo, int u, float4 v) {
+        const uint32_t off = sw128_off(lr + 16 * u, lc);
+        if (PASSES == 3) {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *reinterpret_cast<float4*>(hi + off) = h;
+            *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+            *reinterpret_cast<float4*>(hi + off) = v;
+        }
+    };
+    float4 ra[kRa], rb[kRb];
+    auto fetch = [&](int kb) {
+        const int k0 = kb0 + kb * BK;
+#pragma unroll
+        for (int u = 0; u < kRa; ++u) ra[u] = gload(g.A, g.lda, m0, g.M, k0, kb1, a_vec, u);
+#pragma unroll
+        for (int u = 0; u < kRb; ++u) rb[u] = gload(g.B, g.ldb, n0, g.N, k0, kb1, b_vec, u);
+    };
+    if (n_kb > 0) fetch(0);
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&s_bar[s], uint32_t((kb / kStages - 1) & 1));   // MMAs that read this stage are done
+        unsigned char* st = smem + s * SL::kStageBytes;
+        unsigned char* a_hi = st;
+        unsigned char* b_hi = st + SL::kATile;
+        unsigned char* a_lo = st + SL::kATile + SL::kBTile;
+        unsigned char* b_lo = a_lo + SL::kATile;
+#pragma unroll
+        for (int u = 0; u < kRa; ++u) sstore(a_hi, a_lo, u, ra[u]);
+#pragma unroll
+        for (int u = 0; u < kRb; ++u) sstore(b_hi, b_lo, u, rb[u]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da_hi = make_desc_k_sw128(smem_u32(a_hi)), db_hi = make_desc_k_sw128(smem_u32(b_hi));
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+                const uint64_t adv = uint64_t((k * UK * 4) >> 4);      // 32 bytes per k-step inside the swizzle atom
+                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                if (PASSES == 3) {
+                    const uint64_t da_lo = make_desc_k_sw128(smem_u32(a_lo)), db_lo = make_desc_k_sw128(smem_u32(b_lo));
+                    umma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, acc0);   // small terms first
+                    umma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+                } else {
+                    umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, acc0);
+                }
+            }
+            umma_commit(&s_bar[s]);   // arrives when every MMA issued so far has completed
+        }
+        if (kb + 1 < n_kb) fetch(kb + 1);
+    }
+    // the last commit covers all MMAs of the tile
+    if (n_kb > 0) {
+        const int last = n_kb - 1;
+        mbar_wait(&s_bar[last % kStages], uint32_t((last / kStages) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: thread t <-> row m0 + t (TMEM lane t); columns in chunks of 16 ----
+    const int m = m0 + tid;
+    const uint32_t lane_addr = tmem_d + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= g.N) break;
+        uint32_t r[16];
+        if (n_kb > 0) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(lane_addr + uint32_t(c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            float x = __uint_as_float(r[j]);
+            if (m < g.M && n < g.N) {
+                if (EPI == TC_BIAS) x += g.bias[n];
+                if (EPI == TC_BIAS_RELU) { x += g.bias[n]; x = x > 0.f ? x : 0.f; }                       // lib.rs:882
+                if (EPI == TC_BIAS_TANH) x = tanhf(x + g.bias[n]);                                         // lib.rs:883
+                if (EPI == TC_MUL_DTANH) { const float h = g.aux[size_t(m) * g.ldaux + n]; x *= (1.f - h * h); }   // lib.rs:1034
+                if (EPI == TC_MUL_DRELU) x = g.aux[size_t(m) * g.ldaux + n] > 0.f ? x : 0.f;               // lib.rs:1040
+            }
+            v[j] = x;
+        }
+        if (m < g.M) {
+            if (EPI == TC_ATOMIC) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j < g.N) atomicAdd(&g.C[size_t(m) * g.ldc + n0 + c0 + j], v[j]);
+            } else if (g.C) {
+                float* crow = g.C + size_t(m) * g.ldc + n0 + c0;
+                if (n0 + c0 + 16 <= g.N && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < g.N) crow[j] = v[j];
+                }
+            }
+        }
+        if (EPI != TC_ATOMIC && g.CT && m < g.M) {   // lanes hold consecutive m: coalesced column stores
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < g.N) g.CT[size_t(n0 + c0 + j) * g.ldct + m] = v[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+}
+
+template <int BN, int PASSES, int EPI>
+szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
+    if (g.M <= 0 || g.N <= 0) return SZB_OK;
+    using SL = SmemLayout<BN, PASSES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        attr_set = true;
+    }
+    const int kb_total = (g.K + BK - 1) / BK;
+    split_k = EPI == TC_ATOMIC ? std::max(1, std::min(split_k, kb_total)) : 1;
+    g.k_chunk = ((kb_total + split_k - 1) / split_k) * BK;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.K + g.k_chunk - 1) / g.k_chunk);
+    gemm_tc_kernel<BN, PASSES, EPI><<<grid, kThreadsTc, SL::kTotal, ctx->stream>>>(g);
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+}  // namespace tc
+}  // namespace szb

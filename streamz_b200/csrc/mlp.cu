@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "mlp.cuh"
 
 namespace szb {
@@ -128,7 +129,7 @@ static szb_status gemm(szb_ctx* ctx, int M, int N, int K, const float* A, int ld
 __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, int mode, float* __restrict__ probs,
                                const uint32_t* __restrict__ labels, const float* __restrict__ target_vec,
                                const uint8_t* __restrict__ valid, float* __restrict__ tail, float threshold,
-                               unsigned long long* __restrict__ hist, float* __restrict__ sums) {
+                               unsigned long long* __restrict__ hist, float* __restrict__ sums, float* __restrict__ zT, int ldzT) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -150,7 +151,9 @@ __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, 
         if (mode & 1) probs[size_t(row) * C + c] = p;
         if (mode & 2) {
             const float t = target_vec ? target_vec[c] : (uint32_t(c) == label ? 1.f : 0.f);
-            zr[c] = ok ? p - t : 0.f;                                             // lib.rs:1028
+            const float d3 = ok ? p - t : 0.f;                                    // lib.rs:1028
+            zr[c] = d3;
+            if (zT) zT[size_t(c) * ldzT + row] = d3;
             if (ok && !target_vec && uint32_t(c) == label) atomicAdd(&tail[1], -logf(fmaxf(p, 1e-12f)));  // lib.rs:611-615
         }
         if (mode & 4) { if (p >= best) { best = p; best_c = c; } }                // last maximal element wins
@@ -183,8 +186,8 @@ __global__ void colsum_kernel(const float* __restrict__ D, int rows, int cols, i
 __global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_t* __restrict__ labels_all,
                                   const uint32_t* __restrict__ perm, int B, int n_in, const uint8_t* __restrict__ keep,
                                   int keep_by_row /* keep indexed by window id (1) or by batch row (0) */, float prob,
-                                  unsigned long long key, float* __restrict__ xb, uint32_t* __restrict__ lab,
-                                  uint8_t* __restrict__ valid) {
+                                  unsigned long long key, float* __restrict__ xb, float* __restrict__ xbT, uint32_t* __restrict__ lab,
+                                  uint8_t* __restrict__ valid, float* __restrict__ h1T, int h1, float* __restrict__ h2T, int h2) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -198,12 +201,18 @@ __global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_
             if (!dropout_keep(key, w, uint32_t(i), prob)) v = 0.f;
         }
         xb[size_t(row) * n_in + i] = v;
+        if (xbT) xbT[size_t(i) * B + row] = v;
         any |= (v != 0.f);
     }
     any = __any_sync(0xffffffffu, any);
     if (lane == 0) {
         valid[row] = any ? 1 : 0;
         if (lab) lab[row] = labels_all ? labels_all[w] : 0xffffffffu;
+        if (xbT) {   // row of ones under each transposed activation: the weight-gradient GEMM then yields the bias gradient
+            xbT[size_t(n_in) * B + row] = 1.f;
+            h1T[size_t(h1) * B + row] = 1.f;
+            h2T[size_t(h2) * B + row] = 1.f;
+        }
     }
 }
 
@@ -238,14 +247,77 @@ szb_status net_reserve_rows(szb_net* net, uint64_t rows) {
     SZB_TRY(net->a_z.reserve(rows * net->n_out * 4));
     SZB_TRY(net->d_2.reserve(rows * net->h2 * 4));
     SZB_TRY(net->d_1.reserve(rows * net->h1 * 4));
+    SZB_TRY(net->xbT.reserve(rows * (net->n_in + 1) * 4));   // + the row of ones (bias gradients)
+    SZB_TRY(net->h1T.reserve(rows * (net->h1 + 1) * 4));
+    SZB_TRY(net->h2T.reserve(rows * (net->h2 + 1) * 4));
+    SZB_TRY(net->zT.reserve(rows * net->n_out * 4));
+    SZB_TRY(net->d2T.reserve(rows * net->h2 * 4));
+    SZB_TRY(net->d1T.reserve(rows * net->h1 * 4));
     net->cap_rows = rows;
     return SZB_OK;
 }
 
+// wt1 = w1^T, wt2 = w2^T, wt3 = w3^T in one launch (the weights total < 2 MB and live in L2)
+__global__ void transpose_weights_kernel(const float* __restrict__ P, float* __restrict__ WT, int n_in, int h1, int h2, int n_out,
+                                         size_t off_w2, size_t off_w3, size_t off_wt2, size_t off_wt3) {
+    const size_t n1 = size_t(n_in) * h1, n2 = size_t(h1) * h2, n3 = size_t(h2) * n_out;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += size_t(gridDim.x) * blockDim.x) {
+        if (i < n1) {                       // i indexes wt1[n][k], n < h1, k < n_in
+            const int n = int(i / n_in), k = int(i % n_in);
+            WT[i] = P[size_t(k) * h1 + n];
+        } else if (i < n1 + n2) {
+            const size_t j = i - n1;
+            const int n = int(j / h1), k = int(j % h1);
+            WT[off_wt2 + j] = P[off_w2 + size_t(k) * h2 + n];
+        } else {
+            const size_t j = i - n1 - n2;
+            const int n = int(j / h2), k = int(j % h2);
+            WT[off_wt3 + j] = P[off_w3 + size_t(k) * n_out + n];
+        }
+    }
+}
+
+static szb_status refresh_wt(szb_net* net) {
+    if (!net->wt_dirty) return SZB_OK;
+    szb_ctx* ctx = net->ctx;
+    SZB_TRY(net->wt.reserve(net->n_wt() * 4));
+    const size_t n = net->n_wt();
+    transpose_weights_kernel<<<int(std::min<size_t>((n + 255) / 256, size_t(ctx->sm_count) * 4)), 256, 0, ctx->stream>>>(
+        net->params.as<float>(), net->wt.as<float>(), int(net->n_in), int(net->h1), int(net->h2), int(net->n_out), net->off_w2(),
+        net->off_w3(), net->off_wt2(), net->off_wt3());
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    net->wt_dirty = false;
+    return SZB_OK;
+}
+
+template <int EPI>
+static szb_status gemm_tc(szb_net* net, tc::GemmArgs g, int split_k = 1) {
+    return net->precision == 2 ? tc::launch_gemm_tc<128, 1, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 3, EPI>(net->ctx, g, split_k);
+}
+
 // forward for rows already in d_x (device); leaves logits in a_z; activations in a_h1 / a_h2
-static szb_status forward_rows(szb_net* net, const float* d_x, int B) {
+static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool training = false) {
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
+    if (net->precision != 0) {
+        SZB_TRY(refresh_wt(net));
+        const float* WT = net->wt.as<float>();
+        const int I = int(net->n_in), H1 = int(net->h1), H2 = int(net->h2), C = int(net->n_out);
+        tc::GemmArgs g{};
+        g.A = d_x; g.lda = I; g.B = WT + net->off_wt1(); g.ldb = I; g.C = net->a_h1.as<float>(); g.ldc = H1;
+        g.CT = training ? net->h1T.as<float>() : nullptr; g.ldct = B; g.bias = P + net->off_b1(); g.M = B; g.N = H1; g.K = I;
+        SZB_TRY(gemm_tc<tc::TC_BIAS_RELU>(net, g));
+        g = tc::GemmArgs{};
+        g.A = net->a_h1.as<float>(); g.lda = H1; g.B = WT + net->off_wt2(); g.ldb = H1; g.C = net->a_h2.as<float>(); g.ldc = H2;
+        g.CT = training ? net->h2T.as<float>() : nullptr; g.ldct = B; g.bias = P + net->off_b2(); g.M = B; g.N = H2; g.K = H1;
+        SZB_TRY(gemm_tc<tc::TC_BIAS_TANH>(net, g));
+        g = tc::GemmArgs{};
+        g.A = net->a_h2.as<float>(); g.lda = H2; g.B = WT + net->off_wt3(); g.ldb = H2; g.C = net->a_z.as<float>(); g.ldc = C;
+        g.bias = P + net->off_b3(); g.M = B; g.N = C; g.K = H2;
+        SZB_TRY(gemm_tc<tc::TC_BIAS>(net, g));
+        return SZB_OK;
+    }
     SZB_TRY((gemm<false, false, EPI_BIAS_RELU>(ctx, B, net->h1, net->n_in, d_x, net->n_in, P + net->off_w1(), net->h1,
                                                 net->a_h1.as<float>(), net->h1, P + net->off_b1(), nullptr, 0)));
     SZB_TRY((gemm<false, false, EPI_BIAS_TANH>(ctx, B, net->h2, net->h1, net->a_h1.as<float>(), net->h1, P + net->off_w2(),
@@ -256,13 +328,13 @@ static szb_status forward_rows(szb_net* net, const float* d_x, int B) {
 }
 
 static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, const uint32_t* labels, const float* target_vec,
-                                 const uint8_t* valid, float threshold, unsigned long long* hist, float* sums) {
+                                 const uint8_t* valid, float threshold, unsigned long long* hist, float* sums, float* zT = nullptr) {
     if (B <= 0) return SZB_OK;
     const int wpb = 8;
     float* tail = net->grads.as<float>() + net->n_params();
     softmax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out),
                                                                           int(net->n_out), mode, probs, labels, target_vec,
-                                                                          valid, tail, threshold, hist, sums);
+                                                                          valid, tail, threshold, hist, sums, zT, B);
     SZB_CUDA(cudaGetLastError());
     net->ctx->launches += 1;
     return SZB_OK;
@@ -279,11 +351,43 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
     if (B > 0) {
         const float* xb = net->xb.as<float>();
-        SZB_TRY(forward_rows(net, xb, B));
+        const bool use_tc = net->precision != 0;
+        SZB_TRY(forward_rows(net, xb, B, true));
         SZB_TRY(launch_softmax(net, B, 2, nullptr, net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), 0.f, nullptr,
-                               nullptr));
+                               nullptr, use_tc ? net->zT.as<float>() : nullptr));
         float* d3 = net->a_z.as<float>();
         const int C = int(net->n_out), H1 = int(net->h1), H2 = int(net->h2), I = int(net->n_in);
+        if (use_tc) {
+            auto split_for = [&](int M, int N) {
+                const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+                return std::max(1, ctx->sm_count / tiles);
+            };
+            tc::GemmArgs g{};
+            // gW3[h2][C] = H2^T dZ                                                    (lib.rs:1029-1032)
+            g.A = net->h2T.as<float>(); g.lda = B; g.B = net->zT.as<float>(); g.ldb = B; g.C = G + net->off_w3(); g.ldc = C;
+            g.M = H2 + 1; g.N = C; g.K = B;      // row H2 of the product is sum_b dZ = the b3 gradient, which sits right
+            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H2 + 1, C)));   // behind w3 in the flattened gradient (lib.rs:1033)
+            // d2 = (dZ W3^T) * (1 - H2^2)                                              (lib.rs:1034)
+            g = tc::GemmArgs{};
+            g.A = d3; g.lda = C; g.B = P + net->off_w3(); g.ldb = C; g.C = net->d_2.as<float>(); g.ldc = H2; g.CT = net->d2T.as<float>();
+            g.ldct = B; g.aux = net->a_h2.as<float>(); g.ldaux = H2; g.M = B; g.N = H2; g.K = C;
+            SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, g));
+            // gW2[h1][h2] = H1^T d2                                                    (lib.rs:1035-1037)
+            g = tc::GemmArgs{};
+            g.A = net->h1T.as<float>(); g.lda = B; g.B = net->d2T.as<float>(); g.ldb = B; g.C = G + net->off_w2(); g.ldc = H2;
+            g.M = H1 + 1; g.N = H2; g.K = B;     // + b2 gradient (lib.rs:1038)
+            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H1 + 1, H2)));
+            // d1 = (d2 W2^T) * [H1 > 0]                                                (lib.rs:1039-1040)
+            g = tc::GemmArgs{};
+            g.A = net->d_2.as<float>(); g.lda = H2; g.B = P + net->off_w2(); g.ldb = H2; g.C = net->d_1.as<float>(); g.ldc = H1;
+            g.CT = net->d1T.as<float>(); g.ldct = B; g.aux = net->a_h1.as<float>(); g.ldaux = H1; g.M = B; g.N = H1; g.K = H2;
+            SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, g));
+            // gW1[n_in][h1] = X^T d1                                                   (lib.rs:1041-1043)
+            g = tc::GemmArgs{};
+            g.A = net->xbT.as<float>(); g.lda = B; g.B = net->d1T.as<float>(); g.ldb = B; g.C = G + net->off_w1(); g.ldc = H1;
+            g.M = I + 1; g.N = H1; g.K = B;      // + b1 gradient (lib.rs:1044)
+            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(I + 1, H1)));
+        } else {
         // layer 3
         SZB_TRY((gemm<true, false, EPI_ATOMIC>(ctx, H2, C, B, net->a_h2.as<float>(), H2, d3, C, G + net->off_w3(), C, nullptr,
                                                 nullptr, 0)));
@@ -309,12 +413,14 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         SZB_TRY(colsum(d3, C, G + net->off_b3()));
         SZB_TRY(colsum(net->d_2.as<float>(), H2, G + net->off_b2()));
         SZB_TRY(colsum(net->d_1.as<float>(), H1, G + net->off_b1()));
+        }
     }
     if (ctx->world > 1) SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
     const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
     sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    net->wt_dirty = true;
     return SZB_OK;
 }
 
@@ -324,7 +430,8 @@ static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t
     const int wpb = 8;
     prep_batch_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(
         d_feats, d_labels, d_perm, B, int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
-        net->lab.as<uint32_t>(), net->valid.as<uint8_t>());
+        net->precision != 0 ? net->xbT.as<float>() : nullptr, net->lab.as<uint32_t>(), net->valid.as<uint8_t>(),
+        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2));
     SZB_CUDA(cudaGetLastError());
     net->ctx->launches += 1;
     return SZB_OK;
@@ -409,6 +516,14 @@ szb_status szb_net_dims(const szb_net* net, uint32_t dims[4]) {
 }
 uint32_t szb_net_output_size(const szb_net* net) { return net ? net->n_out : 0; }
 
+szb_status szb_net_set_precision(szb_net* net, int32_t mode) {
+    SZB_REQUIRE(net && mode >= 0 && mode <= 2, "szb_net_set_precision: mode must be 0 (FP32), 1 (3xTF32) or 2 (TF32)");
+    net->precision = mode;
+    net->wt_dirty = true;
+    return SZB_OK;
+}
+int32_t szb_net_get_precision(const szb_net* net) { return net ? net->precision : -1; }
+
 szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t seed) {
     SZB_REQUIRE(net, "szb_net_add_output_class: net is NULL");
     const uint32_t C = net->n_out, H2 = net->h2;
@@ -430,7 +545,8 @@ szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t
     net->params = fresh->params; net->grads = fresh->grads;
     fresh->params = DevBuf(); fresh->grads = DevBuf();
     net->n_out = C + 1;
-    net->a_z.release(); net->cap_rows = 0;
+    net->wt_dirty = true;
+    net->a_z.release(); net->zT.release(); net->cap_rows = 0;
     szb_net_destroy(fresh);
     return SZB_OK;
 }
@@ -439,7 +555,7 @@ void szb_net_destroy(szb_net* net) {
     if (!net) return;
     if (net->ctx) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); }
     for (DevBuf* b : { &net->params, &net->grads, &net->xb, &net->lab, &net->valid, &net->a_h1, &net->a_h2, &net->a_z, &net->d_2,
-                       &net->d_1, &net->stats, &net->perm, &net->hist })
+                       &net->d_1, &net->stats, &net->perm, &net->hist, &net->wt, &net->xbT, &net->h1T, &net->h2T, &net->zT, &net->d2T, &net->d1T })
         b->release();
     delete net;
 }
@@ -494,8 +610,10 @@ szb_status szb_net_train_batch(szb_net* net, const float* x, uint64_t B, const f
     SZB_CUDA(cudaSetDevice(ctx->device));
     SZB_TRY(net_reserve_rows(net, B));
     SZB_TRY(ctx->probs.reserve(size_t(net->n_out) * 4));
-    SZB_CUDA(cudaMemcpyAsync(net->xb.ptr, x, B * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(ctx->x.reserve(B * net->n_in * 4));
+    SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, x, B * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
     SZB_CUDA(cudaMemcpyAsync(ctx->probs.ptr, target, size_t(net->n_out) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(launch_prep(net, ctx->x.as<float>(), nullptr, nullptr, int(B), nullptr, 0, 0.f, 0));
     SZB_CUDA(cudaMemsetAsync(net->valid.ptr, 1, B, ctx->stream));  // the reference's train_batch uses every row it is given
     SZB_TRY(train_step_staged(net, int(B), ctx->probs.as<float>(), lr));
     SZB_CUDA(cudaStreamSynchronize(ctx->stream));

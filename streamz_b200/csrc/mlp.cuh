@@ -10,7 +10,12 @@ struct szb_net {
     szb::DevBuf params, grads;
     // activations / scratch for up to cap_rows rows
     szb::DevBuf xb, lab, valid, a_h1, a_h2, a_z, d_2, d_1, stats, perm, hist;
-    uint64_t cap_rows = 0;
+    // tensor-core path: transposed weights [wt1 (h1 x n_in) | wt2 (h2 x h1) | wt3 (n_out x h2)] and the transposed
+    // activations / deltas ([features][rows]) that make every GEMM of a step "TN" (gemm_tc.cuh)
+    szb::DevBuf wt, xbT, h1T, h2T, zT, d2T, d1T;
+    bool wt_dirty = true;
+    int precision = 1;            // 0 = FP32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = TF32 tensor cores
+    uint64_t cap_rows = 0, cap_rows_t = 0;
     std::vector<std::vector<std::string>> file_lists;  // lib.rs:757, host-side only
 
     size_t off_w1() const { return 0; }
@@ -20,6 +25,10 @@ struct szb_net {
     size_t off_w3() const { return off_b2() + h2; }
     size_t off_b3() const { return off_w3() + size_t(h2) * n_out; }
     size_t n_params() const { return off_b3() + n_out; }
+    size_t off_wt1() const { return 0; }
+    size_t off_wt2() const { return size_t(h1) * n_in; }
+    size_t off_wt3() const { return off_wt2() + size_t(h2) * h1; }
+    size_t n_wt() const { return off_wt3() + size_t(n_out) * h2; }
 };
 
 namespace szb {
