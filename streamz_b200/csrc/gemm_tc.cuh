@@ -103,6 +103,67 @@ struct SmemLayout {
     static constexpr int kTotal = kStages * kStageBytes + 1024;  // + alignment slack
 };
 
+// Epilogue shared by both kernels: thread t <-> row m0 + t (TMEM lane t); columns in chunks of 16.
+template <int BN, int EPI>
+__device__ __forceinline__ void tc_epilogue(const GemmArgs& g, uint32_t tmem_d, int m0, int n0, bool have_acc) {
+    const int tid = threadIdx.x & 127, warp = tid >> 5;      // TMEM lane quarter = warp % 4
+    const int n_kb = have_acc ? 1 : 0;
+    const int m = m0 + tid;
+    const uint32_t lane_addr = tmem_d + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= g.N) break;
+        uint32_t r[16];
+        if (n_kb > 0) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(lane_addr + uint32_t(c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            float x = __uint_as_float(r[j]);
+            if (m < g.M && n < g.N) {
+                if (EPI == TC_BIAS) x += g.bias[n];
+                if (EPI == TC_BIAS_RELU) { x += g.bias[n]; x = x > 0.f ? x : 0.f; }                       // lib.rs:882
+                if (EPI == TC_BIAS_TANH) x = tanhf(x + g.bias[n]);                                         // lib.rs:883
+                if (EPI == TC_MUL_DTANH) { const float h = g.aux[size_t(m) * g.ldaux + n]; x *= (1.f - h * h); }   // lib.rs:1034
+                if (EPI == TC_MUL_DRELU) x = g.aux[size_t(m) * g.ldaux + n] > 0.f ? x : 0.f;               // lib.rs:1040
+            }
+            v[j] = x;
+        }
+        if (m < g.M) {
+            if (EPI == TC_ATOMIC) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j < g.N) atomicAdd(&g.C[size_t(m) * g.ldc + n0 + c0 + j], v[j]);
+            } else if (g.C) {
+                float* crow = g.C + size_t(m) * g.ldc + n0 + c0;
+                if (n0 + c0 + 16 <= g.N && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < g.N) crow[j] = v[j];
+                }
+            }
+        }
+        if (EPI != TC_ATOMIC && g.CT && m < g.M) {   // lanes hold consecutive m: coalesced column stores
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < g.N) g.CT[size_t(n0 + c0 + j) * g.ldct + m] = v[j];
+        }
+    }
+}
+
 // One CTA = one 128 x BN tile of C (x one K split).  128 threads: all of them stage operands; one issues the MMAs;
 // in the epilogue thread t owns accumulator row t (TMEM lane t).
 template <int BN, int PASSES, int EPI>
@@ -218,61 +279,141 @@ __global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: thread t <-> row m0 + t (TMEM lane t); columns in chunks of 16 ----
-    const int m = m0 + tid;
-    const uint32_t lane_addr = tmem_d + (uint32_t(warp * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-        if (n0 + c0 >= g.N) break;
-        uint32_t r[16];
-        if (n_kb > 0) {
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(lane_addr + uint32_t(c0)));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
+    tc_epilogue<BN, EPI>(g, tmem_d, m0, n0, n_kb > 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+}
+
+
+// ---- cp.async-pipelined variant (the one used whenever rows are 16-byte aligned) ---------------------------------------
+// Raw FP32 K-slabs flow global -> shared with cp.async (LDGSTS, zero-filled past the matrix edge) through a ring of
+// kAStages stages, issued two k-blocks ahead of the tensor core; each thread then turns ITS OWN sixteen 16-byte chunks
+// into the hi tile (in place) and the lo tile (3xTF32), so no barrier is needed between the copy and the split.
+constexpr int kAStages = 4;
+
+template <int BN, int PASSES>
+struct SmemLayoutAsync {
+    static constexpr int kATile = BM * BK * 4;
+    static constexpr int kBTile = BN * BK * 4;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kLoBytes = PASSES == 3 ? 2 * kStageBytes : 0;
+    static constexpr int kTotal = kAStages * kStageBytes + kLoBytes;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+constexpr int kThreadsAsync = 256;   // 8 warps stage and split the operands; warp w reads TMEM lanes 32 (w % 4) ..
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const GemmArgs g) {
+    using SL = SmemLayoutAsync<BN, PASSES>;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
+    __shared__ uint64_t s_bar[kAStages];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t smem_base = smem_u32(tc_smem);
+    if ((smem_base & 1023u) != 0) __trap();
+    const uint32_t lo_base = smem_base + kAStages * SL::kStageBytes;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
+    const int n_kb = (kb1 - kb0 + BK - 1) / BK;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kAStages; ++s) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem;
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    constexpr int kRows = kThreadsAsync / 8;                    // rows covered per pass of the CTA (32)
+    constexpr int kRa = BM / kRows, kRb = BN / kRows;           // 4 + 4 sixteen-byte chunks per thread and k-block
+    const int lr = tid >> 3, lc = tid & 7;
+
+    auto issue = [&](int kb) {    // cp.async of k-block kb into stage kb % kAStages
+        const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
+        const int gk = kb0 + kb * BK + lc * 4;
+        const int kleft = kb1 - gk;
+        const uint32_t kbytes = kleft >= 4 ? 16u : (kleft > 0 ? uint32_t(kleft) * 4u : 0u);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int u = 0; u < kRa; ++u) {
+            const int r = lr + kRows * u, gr = m0 + r;
+            const bool ok = gr < g.M && kbytes > 0;
+            cp_async16(st + sw128_off(r, lc), ok ? static_cast<const void*>(g.A + size_t(gr) * g.lda + gk) : static_cast<const void*>(g.A),
+                       ok ? kbytes : 0u);
         }
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            float x = __uint_as_float(r[j]);
-            if (m < g.M && n < g.N) {
-                if (EPI == TC_BIAS) x += g.bias[n];
-                if (EPI == TC_BIAS_RELU) { x += g.bias[n]; x = x > 0.f ? x : 0.f; }                       // lib.rs:882
-                if (EPI == TC_BIAS_TANH) x = tanhf(x + g.bias[n]);                                         // lib.rs:883
-                if (EPI == TC_MUL_DTANH) { const float h = g.aux[size_t(m) * g.ldaux + n]; x *= (1.f - h * h); }   // lib.rs:1034
-                if (EPI == TC_MUL_DRELU) x = g.aux[size_t(m) * g.ldaux + n] > 0.f ? x : 0.f;               // lib.rs:1040
+        for (int u = 0; u < kRb; ++u) {
+            const int r = lr + kRows * u, gr = n0 + r;
+            const bool ok = gr < g.N && kbytes > 0;
+            cp_async16(st + SL::kATile + sw128_off(r, lc),
+                       ok ? static_cast<const void*>(g.B + size_t(gr) * g.ldb + gk) : static_cast<const void*>(g.B), ok ? kbytes : 0u);
+        }
+    };
+    // prologue: two k-blocks in flight
+    for (int j = 0; j < 2; ++j) {
+        if (j < n_kb) issue(j);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < n_kb; ++kb) {
+        // MMAs of k-block kb - 2 done => raw stage (kb + 2) % kAStages and lo buffer kb % 2 are free again
+        if (kb >= 2) mbar_wait(&s_bar[(kb - 2) % kAStages], uint32_t(((kb - 2) / kAStages) & 1));
+        if (kb + 2 < n_kb) issue(kb + 2);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's chunks of k-block kb have landed
+        const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
+        const uint32_t lo = lo_base + (kb & 1) * SL::kStageBytes;
+        if (PASSES == 3) {
+#pragma unroll
+            for (int u = 0; u < kRa + kRb; ++u) {
+                const uint32_t off = (u < kRa ? 0u : uint32_t(SL::kATile)) + sw128_off(lr + kRows * (u < kRa ? u : u - kRa), lc);
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(v.x - h.x), "f"(v.y - h.y), "f"(v.z - h.z),
+                             "f"(v.w - h.w)
+                             : "memory");
             }
-            v[j] = x;
         }
-        if (m < g.M) {
-            if (EPI == TC_ATOMIC) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da_hi = make_desc_k_sw128(st), db_hi = make_desc_k_sw128(st + SL::kATile);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + c0 + j < g.N) atomicAdd(&g.C[size_t(m) * g.ldc + n0 + c0 + j], v[j]);
-            } else if (g.C) {
-                float* crow = g.C + size_t(m) * g.ldc + n0 + c0;
-                if (n0 + c0 + 16 <= g.N && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int k = 0; k < BK / UK; ++k) {
+                const uint64_t adv = uint64_t((k * UK * 4) >> 4);
+                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                if (PASSES == 3) {
+                    const uint64_t da_lo = make_desc_k_sw128(lo), db_lo = make_desc_k_sw128(lo + SL::kATile);
+                    umma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, acc0);
+                    umma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + c0 + j < g.N) crow[j] = v[j];
+                    umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, acc0);
                 }
             }
-        }
-        if (EPI != TC_ATOMIC && g.CT && m < g.M) {   // lanes hold consecutive m: coalesced column stores
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < g.N) g.CT[size_t(n0 + c0 + j) * g.ldct + m] = v[j];
+            umma_commit(&s_bar[kb % kAStages]);
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (n_kb > 0) {
+        const int last = n_kb - 1;
+        mbar_wait(&s_bar[last % kAStages], uint32_t((last / kAStages) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // two warpgroups split the columns: warps 0-3 take [0, BN/2), warps 4-7 take [BN/2, BN)
+    tc_epilogue<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
@@ -282,16 +423,20 @@ template <int BN, int PASSES, int EPI>
 szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
     if (g.M <= 0 || g.N <= 0) return SZB_OK;
     using SL = SmemLayout<BN, PASSES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
-        attr_set = true;
-    }
+    using SLA = SmemLayoutAsync<BN, PASSES>;
     const int kb_total = (g.K + BK - 1) / BK;
     split_k = EPI == TC_ATOMIC ? std::max(1, std::min(split_k, kb_total)) : 1;
     g.k_chunk = ((kb_total + split_k - 1) / split_k) * BK;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.K + g.k_chunk - 1) / g.k_chunk);
-    gemm_tc_kernel<BN, PASSES, EPI><<<grid, kThreadsTc, SL::kTotal, ctx->stream>>>(g);
+    const bool aligned = g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
+    if (aligned) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_async_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLA::kTotal));
+        gemm_tc_async_kernel<BN, PASSES, EPI><<<grid, kThreadsAsync, SLA::kTotal, ctx->stream>>>(g);
+    } else {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        gemm_tc_kernel<BN, PASSES, EPI><<<grid, kThreadsTc, SL::kTotal, ctx->stream>>>(g);
+    }
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return SZB_OK;
