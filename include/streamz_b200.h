@@ -163,6 +163,14 @@ szb_status szb_net_train_epoch_dev(szb_net* net, const float* d_feats, const uin
                                    const uint32_t* perm, uint64_t n_perm, uint32_t batch, float lr, float dropout,
                                    uint64_t seed, uint64_t stream, const uint8_t* d_keep, double* loss_sum,
                                    uint64_t* n_used);
+/* Same with explicit per-step row counts (step i trains on the next step_sizes[i] rows of perm; 0 is allowed).  This is
+ * the multi-GPU form: each rank passes its slice of every global batch (streamz_b200.sharding.shard_batches) and the
+ * step all-reduces [gradient | window count | loss] over the communicator of szb_comm_init, so all ranks must pass the
+ * same n_steps.  loss_sum / n_used are then global. */
+szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, const uint32_t* d_labels, uint64_t n,
+                                         const uint32_t* perm, uint64_t n_perm, const uint32_t* step_sizes, uint32_t n_steps,
+                                         float lr, float dropout, uint64_t seed, uint64_t stream, const uint8_t* d_keep,
+                                         double* loss_sum, uint64_t* n_used);
 /* The dropout stream above, on the host, for callers that need the decisions (tests, oracle): keep[n_rows][n_in]. */
 szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t* rows, uint64_t n_rows, uint32_t n_in,
                                  float prob, uint8_t* keep);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "szb_net_train_batch": (i32, [vp, vp, u64, vp, f32]),
     "szb_net_train_batch_labels": (i32, [vp, vp, vp, u64, f32, vp, P(f64), P(u64)]),
     "szb_net_train_epoch_dev": (i32, [vp, vp, vp, u64, vp, u64, u32, f32, f32, u64, u64, vp, P(f64), P(u64)]),
+    "szb_net_train_epoch_steps_dev": (i32, [vp, vp, vp, u64, vp, u64, vp, u32, f32, f32, u64, u64, vp, P(f64), P(u64)]),
     "szb_dropout_keep_mask": (i32, [u64, u64, vp, u64, u32, f32, vp]),
     "szb_identify_counts": (i32, [vp, vp, u64, f32, vp]),
     "szb_identify_counts_dev": (i32, [vp, vp, u64, f32, vp]),

@@ -379,6 +379,19 @@ def train_epoch(net: SimpleNeuralNet, data: DeviceFeatures, perm, batch: int, lr
     return float(loss.value), int(used.value)
 
 
+def train_epoch_steps(net: SimpleNeuralNet, data: DeviceFeatures, perm, step_sizes, lr: float, dropout: float = 0.0, seed: int = 0,
+                      stream: int = 0) -> Tuple[float, int]:
+    """Multi-GPU form of :func:`train_epoch`: ``perm`` / ``step_sizes`` are this rank's slices of every global batch
+    (``sharding.shard_batches``); returns the GLOBAL loss sum and window count."""
+    perm = np.ascontiguousarray(perm, dtype=np.uint32)
+    sizes = np.ascontiguousarray(step_sizes, dtype=np.uint32)
+    loss, used = C.c_double(), C.c_uint64()
+    N.check(N.lib.szb_net_train_epoch_steps_dev(net._h, C.c_void_p(data.d_feats), C.c_void_p(data.d_labels), data.n, N.ptr(perm),
+                                                len(perm), N.ptr(sizes), len(sizes), float(lr), float(dropout), int(seed), int(stream),
+                                                C.c_void_p(data.d_keep) if data.d_keep is not None else None, C.byref(loss), C.byref(used)))
+    return float(loss.value), int(used.value)
+
+
 def dropout_keep_mask(seed: int, stream: int, rows, n_in: int, prob: float) -> np.ndarray:
     rows = np.ascontiguousarray(rows, dtype=np.uint64)
     keep = np.empty((len(rows), n_in), dtype=np.uint8)

@@ -647,31 +647,52 @@ szb_status szb_net_train_batch_labels(szb_net* net, const float* x, const uint32
     return read_stats(net, loss_sum, n_used);
 }
 
+szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, const uint32_t* d_labels, uint64_t n,
+                                         const uint32_t* perm, uint64_t n_perm, const uint32_t* step_sizes, uint32_t n_steps, float lr,
+                                         float dropout, uint64_t seed, uint64_t stream, const uint8_t* d_keep, double* loss_sum,
+                                         uint64_t* n_used) {
+    SZB_REQUIRE(net, "szb_net_train_epoch_steps_dev: net is NULL");
+    if (loss_sum) *loss_sum = 0.0;
+    if (n_used) *n_used = 0;
+    if (n_steps == 0) return SZB_OK;
+    SZB_REQUIRE(step_sizes && (perm || n_perm == 0), "szb_net_train_epoch_steps_dev: NULL buffer");
+    SZB_REQUIRE(n <= 0xffffffffull, "szb_net_train_epoch_steps_dev: more than 2^32 windows");
+    uint64_t total = 0, max_b = 0;
+    for (uint32_t i = 0; i < n_steps; ++i) {
+        total += step_sizes[i];
+        max_b = std::max<uint64_t>(max_b, step_sizes[i]);
+    }
+    SZB_REQUIRE(total == n_perm, "szb_net_train_epoch_steps_dev: step sizes sum to %llu, perm has %llu rows", (unsigned long long)total,
+                (unsigned long long)n_perm);
+    SZB_REQUIRE(n_perm == 0 || (d_feats && d_labels), "szb_net_train_epoch_steps_dev: NULL device buffer");
+    for (uint64_t i = 0; i < n_perm; ++i)
+        SZB_REQUIRE(perm[i] < n, "szb_net_train_epoch_steps_dev: perm[%llu] = %u out of range", (unsigned long long)i, perm[i]);
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(net_reserve_rows(net, std::max<uint64_t>(1, max_b)));
+    SZB_TRY(net->perm.reserve(std::max<uint64_t>(1, n_perm) * 4));
+    if (n_perm) SZB_CUDA(cudaMemcpyAsync(net->perm.ptr, perm, n_perm * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
+    const unsigned long long key = dropout_key(seed, stream);
+    uint64_t s = 0;
+    for (uint32_t i = 0; i < n_steps; ++i) {
+        const int B = int(step_sizes[i]);
+        SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
+        SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
+        s += step_sizes[i];
+    }
+    return read_stats(net, loss_sum, n_used);   // loss and count are global (all-reduced) in a multi-GPU run
+}
+
 szb_status szb_net_train_epoch_dev(szb_net* net, const float* d_feats, const uint32_t* d_labels, uint64_t n,
                                    const uint32_t* perm, uint64_t n_perm, uint32_t batch, float lr, float dropout, uint64_t seed,
                                    uint64_t stream, const uint8_t* d_keep, double* loss_sum, uint64_t* n_used) {
     SZB_REQUIRE(net, "szb_net_train_epoch_dev: net is NULL");
-    if (loss_sum) *loss_sum = 0.0;
-    if (n_used) *n_used = 0;
-    if (n_perm == 0) return SZB_OK;
-    SZB_REQUIRE(d_feats && d_labels && perm, "szb_net_train_epoch_dev: NULL buffer");
-    SZB_REQUIRE(n <= 0xffffffffull, "szb_net_train_epoch_dev: more than 2^32 windows");
     if (batch == 0) batch = 1;  // lib.rs:602 batch_size.max(1)
-    for (uint64_t i = 0; i < n_perm; ++i)
-        SZB_REQUIRE(perm[i] < n, "szb_net_train_epoch_dev: perm[%llu] = %u out of range", (unsigned long long)i, perm[i]);
-    szb_ctx* ctx = net->ctx;
-    SZB_CUDA(cudaSetDevice(ctx->device));
-    SZB_TRY(net_reserve_rows(net, batch));
-    SZB_TRY(net->perm.reserve(n_perm * 4));
-    SZB_CUDA(cudaMemcpyAsync(net->perm.ptr, perm, n_perm * 4, cudaMemcpyHostToDevice, ctx->stream));
-    SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
-    const unsigned long long key = dropout_key(seed, stream);
-    for (uint64_t s = 0; s < n_perm; s += batch) {
-        const int B = int(std::min<uint64_t>(batch, n_perm - s));
-        SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
-        SZB_TRY(train_step_staged(net, B, nullptr, lr));
-    }
-    return read_stats(net, loss_sum, n_used);
+    std::vector<uint32_t> sizes;
+    for (uint64_t s = 0; s < n_perm; s += batch) sizes.push_back(uint32_t(std::min<uint64_t>(batch, n_perm - s)));
+    return szb_net_train_epoch_steps_dev(net, d_feats, d_labels, n, perm, n_perm, sizes.data(), uint32_t(sizes.size()), lr, dropout, seed,
+                                         stream, d_keep, loss_sum, n_used);
 }
 
 szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t* rows, uint64_t n_rows, uint32_t n_in, float prob,

@@ -1,0 +1,80 @@
+"""Two ranks on two GPUs (one process per GPU, NCCL): batch-parallel training must reproduce the single-GPU epoch, and
+clip-sharded extraction must reproduce the single-GPU features.  Skipped when fewer than 2 GPUs are visible."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _worker(rank, world, port, tmp):
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    import streamz_b200 as sz
+    from streamz_b200.sharding import shard_batches, shard_clips
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)        # plumbing only: carries the NCCL unique id
+    ctx = sz.Context(rank)
+    uid = [sz.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    d = np.load(os.path.join(tmp, "data.npz"))
+    net = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx)
+    data = sz.DeviceFeatures(ctx, d["feats"], d["labels"])
+    tot, cnt = 0.0, 0
+    for epoch in range(2):
+        local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
+        loss, used = sz.train_epoch_steps(net, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
+        tot += loss; cnt += used
+    # extraction: each rank takes its clip range, no collective
+    clips = [d[f"clip{i}"] for i in range(6)]
+    lo, hi = shard_clips([len(c) for c in clips], world)[rank]
+    feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
+    np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+    dist.destroy_process_group()
+
+
+def test_two_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_path):
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    r = np.random.default_rng(9)
+    n = 1000
+    feats = r.standard_normal((n, 60)).astype(np.float32)
+    labels = r.integers(0, 7, n).astype(np.uint32)
+    onet = oracle.Net.init(60, 512, 256, 7, seed=9)
+    perms = [r.permutation(n).astype(np.uint32) for _ in range(2)]
+    clips = [oracle.synth_clip(i % 3, 300 + i, 0.5 + 0.3 * i) for i in range(6)]
+    np.savez(str(tmp_path / "data.npz"), feats=feats, labels=labels, perm0=perms[0], perm1=perms[1],
+             **{f"p{i}": p for i, p in enumerate(onet.params())}, **{f"clip{i}": c for i, c in enumerate(clips)})
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    # single-GPU run of the same epochs
+    net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+    data = sz.DeviceFeatures(ctx, feats, labels)
+    tot, cnt = 0.0, 0
+    for epoch in range(2):
+        loss, used = sz.train_epoch(net, data, perms[epoch], 96, 0.02, dropout=0.2, seed=77, stream=epoch)
+        tot += loss; cnt += used
+    outs = [np.load(str(tmp_path / f"out{k}.npz")) for k in range(2)]
+    for k in range(2):
+        assert int(outs[k]["used"]) == cnt and abs(float(outs[k]["loss"]) - tot) <= 1e-3 * abs(tot)
+        for i, w in enumerate(net.weights()):
+            assert np.abs(outs[k][f"arr_{i}"] - w).max() <= 1e-5          # both replicas == the single-GPU result
+    single = sz.FeatureExtractor(ctx).extract_batch(clips)
+    seen = 0
+    for k in range(2):
+        for i in range(int(outs[k]["lo"]), int(outs[k]["hi"])):
+            assert np.array_equal(outs[k][f"f{i}"], single[i]); seen += 1
+    assert seen == 6
