@@ -1,0 +1,85 @@
+// C++ host-layer test: the reference's own unit test (lib.rs:1832-1851) and the C1 flow (main.rs:500-508, 658-666 ->
+// extract, train_from_feature_map, save/load, identify_speaker_list) written against include/streamz_rs.hpp exactly as a
+// Rust caller writes them against streamz_rs.  Built and run by tests/test_gpu_cpp_host.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "streamz_rs.hpp"
+
+using namespace streamz_rs;
+
+#define REQUIRE(c)                                                        \
+    do {                                                                  \
+        if (!(c)) {                                                       \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                     \
+        }                                                                 \
+    } while (0)
+
+static std::vector<int16_t> tone_clip(int speaker, double seconds) {
+    const size_t n = size_t(seconds * 44100);
+    std::vector<int16_t> s(n);
+    uint32_t lcg = 12345u + speaker;
+    for (size_t i = 0; i < n; ++i) {
+        const double t = double(i) / 44100.0;
+        double x = 0.0;
+        for (int h = 1; h <= 12; ++h) x += std::sin(2 * M_PI * (110.0 + 70.0 * speaker) * h * t) / h;
+        lcg = lcg * 1664525u + 1013904223u;
+        x = 0.3 * x + 0.02 * (double(lcg >> 8) / 8388608.0 - 1.0);
+        s[i] = int16_t(std::lround(std::fmax(-1.0, std::fmin(1.0, x * 0.5)) * 32767.0));
+    }
+    return s;
+}
+
+int main() {
+    // --- weights_change_after_training (lib.rs:1832-1851) ---
+    {
+        SimpleNeuralNet net(4, 3, 2, 2);
+        const std::vector<float> x = { 0.1f, -0.2f, 0.3f, 0.4f };
+        const std::vector<float> before = net.forward(x);
+        net.train_batch({ x }, { 1.0f, 0.0f }, 0.1f);
+        const std::vector<float> after = net.forward(x);
+        REQUIRE(before.size() == 2 && after.size() == 2);
+        REQUIRE(after[0] > before[0]);   // one SGD step towards class 0 must raise its probability
+        REQUIRE(std::fabs(after[0] + after[1] - 1.0f) < 1e-5f);
+    }
+    // --- C1-shaped flow ---
+    FeatureExtractor ex;
+    REQUIRE(ex.extract(std::vector<int16_t>(799)).empty());                      // lib.rs:289
+    std::map<std::string, Windows> fmap;
+    std::vector<std::pair<std::string, size_t>> files;
+    for (int spk = 0; spk < 2; ++spk)
+        for (int k = 0; k < 2; ++k) {
+            const std::string path = "spk" + std::to_string(spk) + "_" + std::to_string(k) + ".wav";
+            fmap[path] = with_thread_extractor([&](const FeatureExtractor& e) { return e.extract(tone_clip(spk, 1.0 + 0.1 * k)); });
+            REQUIRE(fmap[path].size() == szb_num_windows(size_t((1.0 + 0.1 * k) * 44100)) && fmap[path][0].size() == FEATURE_SIZE);
+            files.emplace_back(path, size_t(spk));
+        }
+    SimpleNeuralNet net(FEATURE_SIZE, 512, 256, 2, 1);
+    const float l0 = train_from_feature_map(net, fmap, files, 1, 0.01f, DEFAULT_DROPOUT, 8, 1);
+    const float l1 = train_from_feature_map(net, fmap, files, 6, 0.01f, DEFAULT_DROPOUT, 8, 2);
+    REQUIRE(std::isfinite(l0) && l1 < l0);
+    const auto who0 = identify_speaker_list(net, tone_clip(0, 1.0), 0.5f, ex);
+    const auto who1 = identify_speaker_list(net, tone_clip(1, 1.0), 0.5f, ex);
+    REQUIRE(!who0.empty() && who0[0] == 0);
+    REQUIRE(!who1.empty() && who1[0] == 1);
+    REQUIRE(identify_speaker(net, tone_clip(1, 0.7), ex) == 1);
+    REQUIRE(identify_speaker_with_threshold(net, tone_clip(0, 0.7), 0.5f, ex).value_or(99) == 0);
+    REQUIRE(!identify_speaker_with_threshold(net, tone_clip(0, 0.7), 1.5f, ex).has_value());
+    // --- save / load round trip (lib.rs:1081-1282) ---
+    const char* path = "/tmp/streamz_b200_cpp_model.npz";
+    net.save(path);
+    SimpleNeuralNet back = SimpleNeuralNet::load(path);
+    REQUIRE(back.output_size() == 2);
+    const auto p0 = net.forward(fmap.begin()->second[3]), p1 = back.forward(fmap.begin()->second[3]);
+    REQUIRE(p0[0] == p1[0] && p0[1] == p1[1]);
+    net.add_output_class();
+    REQUIRE(net.output_size() == 3 && net.forward(fmap.begin()->second[0]).size() == 3);
+    // resampler contract: identity at 44.1 kHz, length floor(n * 44100 / rate)
+    const std::vector<int16_t> c = tone_clip(0, 0.25);
+    REQUIRE(resample_to_44100(c, 44100) == c);
+    REQUIRE(resample_to_44100(std::vector<int16_t>(16000, 100), 16000).size() == 44100);
+    std::puts("host_api_test ok");
+    return 0;
+}
