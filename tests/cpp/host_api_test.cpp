@@ -57,8 +57,12 @@ int main() {
             files.emplace_back(path, size_t(spk));
         }
     SimpleNeuralNet net(FEATURE_SIZE, 512, 256, 2, 1);
+    // train_from_feature_map visits the files one after the other (lib.rs:643-658); several one-epoch rounds interleave
+    // the two speakers so that the last file does not wipe out the first
     const float l0 = train_from_feature_map(net, fmap, files, 1, 0.01f, DEFAULT_DROPOUT, 8, 1);
-    const float l1 = train_from_feature_map(net, fmap, files, 6, 0.01f, DEFAULT_DROPOUT, 8, 2);
+    float l1 = l0;
+    for (int round = 0; round < 12; ++round) l1 = train_from_feature_map(net, fmap, files, 1, 0.01f, DEFAULT_DROPOUT, 8, 2 + round);
+    std::printf("loss %.4f -> %.4f\n", l0, l1);
     REQUIRE(std::isfinite(l0) && l1 < l0);
     const auto who0 = identify_speaker_list(net, tone_clip(0, 1.0), 0.5f, ex);
     const auto who1 = identify_speaker_list(net, tone_clip(1, 1.0), 0.5f, ex);
