@@ -404,6 +404,11 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     }
     seg_begin[n_chunks] = segs.size();
     SZB_TRY(upload_segments(ctx, segs, uint32_t(n_chunks)));
+    // 128-bit PCM loads need every clip to start on a 16-byte boundary (always true after the resampler: its output
+    // rows are padded to 8 samples; true for caller-packed 44.1 kHz batches whose offsets are multiples of 8)
+    bool aligned16 = (reinterpret_cast<uintptr_t>(d_pcm44) & 15) == 0;
+    for (uint32_t c = 0; c < n_clips && aligned16; ++c)
+        if (woff[c + 1] > woff[c] && (seg_off[c] & 7) != 0) aligned16 = false;
 
     if (piped) {
         while (ctx->pipe_events.size() < 2 * n_chunks + 1) {
@@ -431,7 +436,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
             for (uint32_t c = c0; c < c1; ++c) max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
             SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
         }
-        SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats));
+        SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats, aligned16));
         if (piped) {
             SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
             SZB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_events[2 * k + 1], 0));

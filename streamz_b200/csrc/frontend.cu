@@ -50,7 +50,7 @@ constexpr size_t kSmemS = size_t(kHalf) * kTile * 8;                    // 102 4
 constexpr size_t kSmemP = size_t(kBins) * kTile * 4;                    // 51 328
 constexpr size_t kSmemE = size_t(kMels + kMaxMelTasks) * kTile * 4;     // 9 472: ln energies + partial sums
 constexpr size_t kSmemRing = size_t(kMfcc) * kRing * 4;                 // 5 120
-constexpr size_t kSmemRed = size_t(kWarps) * 32 * 4;                    // 2 560
+constexpr size_t kSmemRed = size_t(2 * kWarps) * 32 * 4;                // 5 120: per-warp sum and sum of squares
 constexpr size_t kSmemOut = size_t(kTile) * kFeat * 4;                  // 7 680
 constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 constexpr size_t kOffPcm = 0;
@@ -63,9 +63,12 @@ constexpr size_t kOffOut = align16(kOffRed + kSmemRed);
 constexpr size_t kSmemTotal = align16(kOffOut + kSmemOut);
 static_assert(kSmemTotal <= 227 * 1024, "front-end tile does not fit in shared memory");
 
-__device__ __forceinline__ float s16lo(uint32_t v) { return float(int(short(v & 0xffffu))); }
-__device__ __forceinline__ float s16hi(uint32_t v) { return float(int(v) >> 16); }
+// (x[2n], x[2n+1]) packed in one word -> two floats; cvt.rn.f32.s16 reads the 16-bit halves directly
+__device__ __forceinline__ void s16x2_to_f32(uint32_t v, float& lo, float& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.s16 %0, l;\n\tcvt.rn.f32.s16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(v));
+}
 
+template <bool kAligned16>   // every segment's first sample is 16-byte aligned: 128-bit loads, no scalar fallback code
 __global__ void __launch_bounds__(kThreads, 1)
 extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs, uint32_t n_segs,
                unsigned int* __restrict__ queue, float* __restrict__ out) {
@@ -101,7 +104,6 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
         constexpr int kVecPerHop = kHop / 8;                       // 50 uint4 per hop
         constexpr int kVecPerTile = kPcmRows * kVecPerHop;         // 1650
         constexpr int kPre = (kVecPerTile + kThreads - 1) / kThreads;  // 3
-        const bool aligned16 = (reinterpret_cast<uintptr_t>(clip) & 15) == 0;
         uint4 pre[kPre];
         auto fetch_tile = [&](uint32_t ta) {
             const uint32_t tnf = min(uint32_t(kTile), f_hi - ta);
@@ -111,7 +113,7 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 const int q = tid + r * kThreads;
                 pre[r] = make_uint4(0u, 0u, 0u, 0u);
                 if (q < int(tnf + 1) * kVecPerHop) {
-                    if (aligned16) {
+                    if (kAligned16) {
                         pre[r] = __ldg(reinterpret_cast<const uint4*>(src) + q);
                     } else {
                         const int16_t* s8 = src + size_t(q) * 8;
@@ -149,8 +151,7 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 for (int n2 = 0; n2 < kR; ++n2) {
                     // z[n] lives in hop `lane` for n < 200 and in hop `lane + 1` (row stride 201 = 200 + 1) above
                     const uint32_t v = pw[kR * n2 + (n2 >= kR / 2 ? 1 : 0)];
-                    re[n2] = s16lo(v);
-                    im[n2] = s16hi(v);
+                    s16x2_to_f32(v, re[n2], im[n2]);
                 }
                 dft20(re, im);
                 float2* dst = s_S + n1 * kTile + lane;
@@ -247,9 +248,10 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             }
             __syncthreads();
 
-            // ---- 6. DCT-II, first 20 coefficients: warp = coefficient, lane = frame (lib.rs:312-315) -------------------
+            // ---- 6. DCT-II, first 20 coefficients: warp = coefficient j, lane = frame (lib.rs:312-315).  Row j of the MFCC
+            //         ring is written and read by warp j only, so the delta stage below needs no block barrier. ------------
+            const int j = warp;
             {
-                const int j = warp;
                 const float* dj = c_dct + j * kMels;
                 float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
@@ -259,7 +261,7 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 }
                 if (uint32_t(lane) < nf) s_ring[j * kRing + ((a + lane) & (kRing - 1))] = acc0 + acc1;
             }
-            __syncthreads();
+            __syncwarp();
 
             // ---- 7. delta, delta-delta, z-score and store for the windows whose +-2 neighbours are now known ----------
             const bool last = a + nf >= f_hi;
@@ -267,7 +269,6 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             for (uint32_t w0 = emit_next; w0 < lim; w0 += kTile) {
                 const uint32_t w = w0 + lane;
                 const bool valid = w < lim;
-                const int j = warp;
                 float c0 = 0.f, d1 = 0.f, d2 = 0.f;
                 if (valid) {
                     const int hi = int(n_total) - 1;
@@ -281,30 +282,30 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                     const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;       // delta at clamp(w-1)
                     d2 = (dp - dm) * 0.5f;                                         // lib.rs:322
                 }
+                // per-window sums over the 60 values: each warp contributes its coefficient's three entries
                 s_red[warp * 32 + lane] = c0 + d1 + d2;
+                s_red[(kWarps + warp) * 32 + lane] = fmaf(c0, c0, fmaf(d1, d1, d2 * d2));
                 __syncthreads();
-                float sum = 0.f;
+                float sum = 0.f, sq = 0.f;
 #pragma unroll
-                for (int q = 0; q < kWarps; ++q) sum += s_red[q * 32 + lane];
+                for (int q = 0; q < kWarps; ++q) {
+                    sum += s_red[q * 32 + lane];
+                    sq += s_red[(kWarps + q) * 32 + lane];
+                }
                 const float mean = sum / float(kFeat);                             // lib.rs:328
-                __syncthreads();
-                const float e0 = c0 - mean, e1 = d1 - mean, e2 = d2 - mean;
-                s_red[warp * 32 + lane] = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
-                __syncthreads();
-                float var = 0.f;
-#pragma unroll
-                for (int q = 0; q < kWarps; ++q) var += s_red[q * 32 + lane];
-                var = var / float(kFeat);                                          // lib.rs:329-336
+                // population variance (lib.rs:329-336) as E[v^2] - mean^2: one reduction instead of two; the 60 values
+                // span |c0| >> |mean|, so there is no cancellation (error ~1e-6 relative, tests hold 1e-4 absolute)
+                const float var = fmaxf(sq / float(kFeat) - mean * mean, 0.f);
                 const float sd = fmaxf(sqrtf(var), 1e-6f);                         // lib.rs:337
-                s_out[lane * kFeat + j] = e0 / sd;                                 // lib.rs:338-340
-                s_out[lane * kFeat + kMfcc + j] = e1 / sd;
-                s_out[lane * kFeat + 2 * kMfcc + j] = e2 / sd;
+                s_out[lane * kFeat + j] = (c0 - mean) / sd;                        // lib.rs:338-340
+                s_out[lane * kFeat + kMfcc + j] = (d1 - mean) / sd;
+                s_out[lane * kFeat + 2 * kMfcc + j] = (d2 - mean) / sd;
                 __syncthreads();
                 const uint32_t nvalid = min(uint32_t(kTile), lim - w0);
                 float4* dst = reinterpret_cast<float4*>(out_clip + size_t(w0) * kFeat);
                 const float4* srcv = reinterpret_cast<const float4*>(s_out);
                 for (uint32_t i = tid; i < nvalid * (kFeat / 4); i += kThreads) dst[i] = srcv[i];
-                __syncthreads();
+                if (w0 + kTile < lim) __syncthreads();   // a second chunk (clip end only) reuses s_red / s_out
             }
             emit_next = max(emit_next, lim);
         }
@@ -489,7 +490,8 @@ szb_status upload_frontend_tables() {
         SZB_CUDA(cudaMemcpyToSymbol(c_mel_warp_begin, warp_begin, sizeof warp_begin));
         SZB_CUDA(cudaMemcpyToSymbol(c_mel_part_begin, part_begin, sizeof part_begin));
     }
-    SZB_CUDA(cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
+    SZB_CUDA(cudaFuncSetAttribute(extract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
+    SZB_CUDA(cudaFuncSetAttribute(extract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
     return SZB_OK;
 }
 
@@ -533,7 +535,8 @@ szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint3
 }
 
 // Launches the extraction kernel over segments [seg_begin, seg_begin + n_segs) of the uploaded table, queue `queue`.
-szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats) {
+szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats,
+                          bool aligned16) {
     if (n_segs == 0) return SZB_OK;
     const int grid = int(std::min<size_t>(n_segs, size_t(ctx->sm_count)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -542,8 +545,12 @@ szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin
         SZB_CUDA(cudaEventCreate(&e1));
         SZB_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    extract_kernel<<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
-                                                               ctx->counter.as<unsigned int>() + queue, d_feats);
+    if (aligned16)
+        extract_kernel<true><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
+                                                                         ctx->counter.as<unsigned int>() + queue, d_feats);
+    else
+        extract_kernel<false><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
+                                                                          ctx->counter.as<unsigned int>() + queue, d_feats);
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (ctx->ktime_on) {

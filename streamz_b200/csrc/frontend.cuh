@@ -22,7 +22,8 @@ szb_status upload_frontend_tables();
 void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_t clip_begin, uint32_t clip_end, int sm_count,
                     std::vector<Segment>& segs);
 szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint32_t n_queues);
-szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats);
+szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats,
+                          bool aligned16);
 szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
                            uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out);
 szb_status launch_downmix(szb_ctx* ctx, const int16_t* d_in, uint64_t n_in, uint32_t ch, int16_t* d_out, uint64_t n_out);
