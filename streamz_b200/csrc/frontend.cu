@@ -74,7 +74,7 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                unsigned int* __restrict__ queue, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_pcm = reinterpret_cast<uint32_t*>(smem + kOffPcm);
-    float2* s_S = reinterpret_cast<float2*>(smem + kOffS);
+    cpx* s_S = reinterpret_cast<cpx*>(smem + kOffS);          // one 64-bit (re, im) pair per element
     float* s_P = reinterpret_cast<float*>(smem + kOffP);
     float* s_E = reinterpret_cast<float*>(smem + kOffE);
     float* s_ring = reinterpret_cast<float*>(smem + kOffRing);
@@ -146,21 +146,23 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             {
                 const int n1 = warp;
                 const uint32_t* pw = s_pcm + lane * kHopStride + n1;
-                float re[kR], im[kR];
+                cpx z[kR];
 #pragma unroll
                 for (int n2 = 0; n2 < kR; ++n2) {
                     // z[n] lives in hop `lane` for n < 200 and in hop `lane + 1` (row stride 201 = 200 + 1) above
                     const uint32_t v = pw[kR * n2 + (n2 >= kR / 2 ? 1 : 0)];
-                    s16x2_to_f32(v, re[n2], im[n2]);
+                    float lo, hi;
+                    s16x2_to_f32(v, lo, hi);
+                    z[n2] = cpack(lo, hi);
                 }
-                dft20(re, im);
-                float2* dst = s_S + n1 * kTile + lane;
-                dst[0] = make_float2(re[0], im[0]);
+                dft20(z);
+                cpx* dst = s_S + n1 * kTile + lane;
+                dst[0] = z[0];
                 const float2* tw = c_tw400 + n1 * kR;
 #pragma unroll
                 for (int k2 = 1; k2 < kR; ++k2) {
                     const float2 w = tw[k2];
-                    dst[k2 * kR * kTile] = make_float2(fmaf(re[k2], w.x, -(im[k2] * w.y)), fmaf(re[k2], w.y, im[k2] * w.x));
+                    dst[k2 * kR * kTile] = cmul_tw(z[k2], w.x, w.y);
                 }
             }
             __syncthreads();
@@ -168,17 +170,13 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
 
             // ---- 3. stage B: warp = k2, lane = frame.  20-point DFT over n1, in place: row k2*20 + k1 = Z[k2 + 20 k1] --
             {
-                float2* col = s_S + warp * kR * kTile + lane;
-                float re[kR], im[kR];
+                cpx* col = s_S + warp * kR * kTile + lane;
+                cpx z[kR];
 #pragma unroll
-                for (int n1 = 0; n1 < kR; ++n1) {
-                    const float2 v = col[n1 * kTile];
-                    re[n1] = v.x;
-                    im[n1] = v.y;
-                }
-                dft20(re, im);
+                for (int n1 = 0; n1 < kR; ++n1) z[n1] = col[n1 * kTile];
+                dft20(z);
 #pragma unroll
-                for (int k1 = 0; k1 < kR; ++k1) col[k1 * kTile] = make_float2(re[k1], im[k1]);
+                for (int k1 = 0; k1 < kR; ++k1) col[k1 * kTile] = z[k1];
             }
             __syncthreads();
 
@@ -187,33 +185,29 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             {
                 const int k2 = warp;
                 if (k2 == 0) {
-                    const float2 z = s_S[lane];
-                    const float p0 = z.x + z.y, p1 = z.x - z.y;
+                    const cpx z = s_S[lane];
+                    const float p0 = cre(z) + cim(z), p1 = cre(z) - cim(z);
                     s_P[lane] = 4.f * p0 * p0;
                     s_P[400 * kTile + lane] = 4.f * p1 * p1;
 #pragma unroll
                     for (int k1 = 1; k1 <= 10; ++k1) {             // k = 20 k1, mirror row 20 - k1 (k1 = 10: itself)
-                        const float2 za = s_S[k1 * kTile + lane];
-                        const float2 zb = s_S[(kR - k1) * kTile + lane];
                         const float2 w = c_tw800[kR * k1];
                         float pk, pmk;
-                        split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
+                        split_pair_power(s_S[k1 * kTile + lane], s_S[(kR - k1) * kTile + lane], w.x, w.y, pk, pmk);
                         s_P[(kR * k1) * kTile + lane] = pk;
                         s_P[(kHalf - kR * k1) * kTile + lane] = pmk;
                     }
                 } else {
-                    const float2* ra = s_S + (k2 * kR) * kTile + lane;
-                    const float2* rb = s_S + ((kR - k2) * kR + kR - 1) * kTile + lane;
+                    const cpx* ra = s_S + (k2 * kR) * kTile + lane;
+                    const cpx* rb = s_S + ((kR - k2) * kR + kR - 1) * kTile + lane;
                     const float2* tw = c_tw800 + k2;
                     float* pa = s_P + k2 * kTile + lane;
                     float* pb = s_P + (kHalf - k2) * kTile + lane;
 #pragma unroll
                     for (int k1 = 0; k1 < 10; ++k1) {
-                        const float2 za = ra[k1 * kTile];
-                        const float2 zb = rb[-k1 * kTile];
                         const float2 w = tw[kR * k1];
                         float pk, pmk;
-                        split_pair_power(za.x, za.y, zb.x, zb.y, w.x, w.y, pk, pmk);
+                        split_pair_power(ra[k1 * kTile], rb[-k1 * kTile], w.x, w.y, pk, pmk);
                         pa[(kR * k1) * kTile] = pk;
                         pb[-(kR * k1) * kTile] = pmk;
                     }

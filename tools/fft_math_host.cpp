@@ -16,52 +16,49 @@ extern "C" {
 void host_frame_power(const int16_t* frame, float* power4) {
     static const std::vector<float> tw400 = twiddles_400();
     static const std::vector<float> tw800 = twiddles_800_half();
-    std::vector<float> sr(kHalf), si(kHalf);
+    std::vector<cpx> S(kHalf);
     // stage A: for each n1, 20-point DFT over n2 of z[n1 + 20 n2], twiddle W400^{n1 k2}, store row k2*20 + n1
     for (int n1 = 0; n1 < kR; ++n1) {
-        float re[20], im[20];
+        cpx z[20];
         for (int n2 = 0; n2 < kR; ++n2) {
             const int n = n1 + kR * n2;
-            re[n2] = float(frame[2 * n]);
-            im[n2] = float(frame[2 * n + 1]);
+            z[n2] = cpack(float(frame[2 * n]), float(frame[2 * n + 1]));
         }
-        dft20(re, im);
-        for (int k2 = 0; k2 < kR; ++k2) {
-            const float wr = tw400[(n1 * kR + k2) * 2], wi = tw400[(n1 * kR + k2) * 2 + 1];
-            sr[k2 * kR + n1] = re[k2] * wr - im[k2] * wi;
-            si[k2 * kR + n1] = re[k2] * wi + im[k2] * wr;
+        dft20(z);
+        S[n1] = z[0];
+        for (int k2 = 1; k2 < kR; ++k2) {
+            const float* w = &tw400[(n1 * kR + k2) * 2];
+            S[k2 * kR + n1] = cmul_tw(z[k2], w[0], w[1]);
         }
     }
     // stage B: for each k2, 20-point DFT over n1 in place: row k2*20 + k1 holds Z[k2 + 20 k1]
     for (int k2 = 0; k2 < kR; ++k2) {
-        float re[20], im[20];
-        for (int n1 = 0; n1 < kR; ++n1) { re[n1] = sr[k2 * kR + n1]; im[n1] = si[k2 * kR + n1]; }
-        dft20(re, im);
-        for (int k1 = 0; k1 < kR; ++k1) { sr[k2 * kR + k1] = re[k1]; si[k2 * kR + k1] = im[k1]; }
+        cpx z[20];
+        for (int n1 = 0; n1 < kR; ++n1) z[n1] = S[k2 * kR + n1];
+        dft20(z);
+        for (int k1 = 0; k1 < kR; ++k1) S[k2 * kR + k1] = z[k1];
     }
     // real split + power
     {
-        const float zr = sr[row_of_bin(0)], zi = si[row_of_bin(0)];
+        const float zr = cre(S[row_of_bin(0)]), zi = cim(S[row_of_bin(0)]);
         const float a = zr + zi, b = zr - zi;
         power4[0] = 4.f * a * a;
         power4[400] = 4.f * b * b;
     }
     for (int k = 1; k <= 200; ++k) {
-        const int ra = row_of_bin(k), rb = row_of_bin(kHalf - k);
+        const float* w = &tw800[k * 2];
         float pk, pmk;
-        split_pair_power(sr[ra], si[ra], sr[rb], si[rb], tw800[2 * k], tw800[2 * k + 1], pk, pmk);
+        split_pair_power(S[row_of_bin(k)], S[row_of_bin(kHalf - k)], w[0], w[1], pk, pmk);
         power4[k] = pk;
         power4[kHalf - k] = pmk;  // k == 200 writes the same value twice
     }
 }
 
 void host_dft20(float* re, float* im) {
-    float r[20], i[20];
-    std::memcpy(r, re, sizeof r);
-    std::memcpy(i, im, sizeof i);
-    dft20(r, i);
-    std::memcpy(re, r, sizeof r);
-    std::memcpy(im, i, sizeof i);
+    cpx z[20];
+    for (int i = 0; i < 20; ++i) z[i] = cpack(re[i], im[i]);
+    dft20(z);
+    for (int i = 0; i < 20; ++i) { re[i] = cre(z[i]); im[i] = cim(z[i]); }
 }
 
 void host_mel_dense(float* out /*26*401*/) {
