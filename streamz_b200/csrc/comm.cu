@@ -69,6 +69,28 @@ szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n) {
     return SZB_OK;
 }
 
+// All-reduce of one gradient slice on the communication stream, ordered after everything enqueued so far on the
+// context's stream: the reduction of layer-3 gradients then runs while the backward GEMMs of layers 2 and 1 execute.
+szb_status comm_allreduce_overlapped(szb_ctx* ctx, float* buf, size_t n) {
+    if (ctx->world <= 1 || n == 0) return SZB_OK;
+    SZB_REQUIRE(ctx->nccl_comm, "all-reduce requested but szb_comm_init was not called");
+    if (!ctx->comm_stream) SZB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_comm) SZB_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    SZB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->stream));
+    SZB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm, 0));
+    SZB_NCCL(g_nccl.AllReduce(buf, buf, n, 7, 0, ctx->nccl_comm, ctx->comm_stream));
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+// The context's stream waits for every overlapped all-reduce issued so far.
+szb_status comm_join(szb_ctx* ctx) {
+    if (ctx->world <= 1 || !ctx->comm_stream) return SZB_OK;
+    SZB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+    SZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    return SZB_OK;
+}
+
 }  // namespace szb
 
 using namespace szb;
@@ -104,6 +126,8 @@ szb_status szb_comm_destroy(szb_ctx* ctx) {
         g_nccl.CommDestroy(ctx->nccl_comm);
     }
     ctx->nccl_comm = nullptr;
+    if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
+    if (ctx->ev_comm) { cudaEventDestroy(ctx->ev_comm); ctx->ev_comm = nullptr; }
     ctx->world = 1;
     ctx->rank = 0;
     return SZB_OK;

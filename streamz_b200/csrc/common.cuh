@@ -76,5 +76,7 @@ struct szb_ctx {
     uint32_t taps_rate = 0;  // rate the taps buffer currently holds
     // NCCL (loaded lazily with dlopen; see comm.cu)
     void* nccl_comm = nullptr;
+    cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the rest of the backward pass
+    cudaEvent_t ev_comm = nullptr;
     int rank = 0, world = 1;
 };

@@ -342,6 +342,8 @@ static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, co
 
 // One optimiser step on the B rows staged in net->xb (+ lab / valid): forward, CE backward, [all-reduce], SGD.
 szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n);  // comm.cu
+szb_status comm_allreduce_overlapped(szb_ctx* ctx, float* buf, size_t n);
+szb_status comm_join(szb_ctx* ctx);
 
 static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr) {
     szb_ctx* ctx = net->ctx;
@@ -349,6 +351,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     float* G = net->grads.as<float>();
     const size_t np = net->n_params();
     SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
+    bool reduced = false;   // gradient slices already all-reduced (overlapped) inside the backward pass
     if (B > 0) {
         const float* xb = net->xb.as<float>();
         const bool use_tc = net->precision != 0;
@@ -367,6 +370,8 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             g.A = net->h2T.as<float>(); g.lda = B; g.B = net->zT.as<float>(); g.ldb = B; g.C = G + net->off_w3(); g.ldc = C;
             g.M = H2 + 1; g.N = C; g.K = B;      // row H2 of the product is sum_b dZ = the b3 gradient, which sits right
             SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H2 + 1, C)));   // behind w3 in the flattened gradient (lib.rs:1033)
+            // multi-GPU: [w3 | b3 | n_used, loss] is final -> reduce it across ranks while layers 2 and 1 run
+            SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w3(), np + kGradTail - net->off_w3()));
             // d2 = (dZ W3^T) * (1 - H2^2)                                              (lib.rs:1034)
             g = tc::GemmArgs{};
             g.A = d3; g.lda = C; g.B = P + net->off_w3(); g.ldb = C; g.C = net->d_2.as<float>(); g.ldc = H2; g.CT = net->d2T.as<float>();
@@ -377,6 +382,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             g.A = net->h1T.as<float>(); g.lda = B; g.B = net->d2T.as<float>(); g.ldb = B; g.C = G + net->off_w2(); g.ldc = H2;
             g.M = H1 + 1; g.N = H2; g.K = B;     // + b2 gradient (lib.rs:1038)
             SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H1 + 1, H2)));
+            SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w2(), net->off_w3() - net->off_w2()));
             // d1 = (d2 W2^T) * [H1 > 0]                                                (lib.rs:1039-1040)
             g = tc::GemmArgs{};
             g.A = net->d_2.as<float>(); g.lda = H2; g.B = P + net->off_w2(); g.ldb = H2; g.C = net->d_1.as<float>(); g.ldc = H1;
@@ -387,6 +393,9 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             g.A = net->xbT.as<float>(); g.lda = B; g.B = net->d1T.as<float>(); g.ldb = B; g.C = G + net->off_w1(); g.ldc = H1;
             g.M = I + 1; g.N = H1; g.K = B;      // + b1 gradient (lib.rs:1044)
             SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(I + 1, H1)));
+            SZB_TRY(comm_allreduce_overlapped(ctx, G, net->off_w2()));
+            SZB_TRY(comm_join(ctx));
+            reduced = true;
         } else {
         // layer 3
         SZB_TRY((gemm<true, false, EPI_ATOMIC>(ctx, H2, C, B, net->a_h2.as<float>(), H2, d3, C, G + net->off_w3(), C, nullptr,
@@ -415,7 +424,17 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         SZB_TRY(colsum(net->d_1.as<float>(), H1, G + net->off_b1()));
         }
     }
-    if (ctx->world > 1) SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
+    if (ctx->world > 1 && !reduced) {
+        if (net->precision != 0) {
+            // a rank whose slice of this batch is empty must still issue the SAME collectives as its peers
+            SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w3(), np + kGradTail - net->off_w3()));
+            SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w2(), net->off_w3() - net->off_w2()));
+            SZB_TRY(comm_allreduce_overlapped(ctx, G, net->off_w2()));
+            SZB_TRY(comm_join(ctx));
+        } else {
+            SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
+        }
+    }
     const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
     sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
     SZB_CUDA(cudaGetLastError());
