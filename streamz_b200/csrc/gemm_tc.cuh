@@ -305,13 +305,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-constexpr int kThreadsAsync = 256;   // 8 warps stage and split the operands; warp w reads TMEM lanes 32 (w % 4) ..
+constexpr int kProducerThreads = 256;                    // warps 0-7: stage + split operands, then run the epilogue
+constexpr int kThreadsAsync = kProducerThreads + 32;      // warp 8: one elected lane issues the tcgen05.mma stream
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised pipeline, no CTA-wide barrier inside the K loop:
+//   producers (256 threads): wait free[(kb+2)%4] -> cp.async k-block kb+2 -> wait own copies of k-block kb -> split into
+//                            hi (in place) / lo tiles -> fence.proxy.async -> arrive on full[kb%4]
+//   issuer (1 thread):       wait full[kb%4] -> tcgen05.mma x 4 (x3 passes) -> tcgen05.commit -> free[kb%4]
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const GemmArgs g) {
     using SL = SmemLayoutAsync<BN, PASSES>;
     extern __shared__ __align__(1024) unsigned char tc_smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
-    __shared__ uint64_t s_bar[kAStages];
+    __shared__ uint64_t s_full[kAStages], s_free[kAStages];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -327,7 +336,10 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < kAStages; ++s) mbar_init(&s_bar[s], 1);
+        for (int s = 0; s < kAStages; ++s) {
+            mbar_init(&s_full[s], kProducerThreads);
+            mbar_init(&s_free[s], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -335,60 +347,68 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem;
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-    constexpr int kRows = kThreadsAsync / 8;                    // rows covered per pass of the CTA (32)
-    constexpr int kRa = BM / kRows, kRb = BN / kRows;           // 4 + 4 sixteen-byte chunks per thread and k-block
-    const int lr = tid >> 3, lc = tid & 7;
 
-    auto issue = [&](int kb) {    // cp.async of k-block kb into stage kb % kAStages
-        const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
-        const int gk = kb0 + kb * BK + lc * 4;
-        const int kleft = kb1 - gk;
-        const uint32_t kbytes = kleft >= 4 ? 16u : (kleft > 0 ? uint32_t(kleft) * 4u : 0u);
+    if (warp < kProducerThreads / 32) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        constexpr int kRows = kProducerThreads / 8;                 // rows covered per pass (32)
+        constexpr int kRa = BM / kRows, kRb = BN / kRows;           // 4 + 4 sixteen-byte chunks per thread and k-block
+        const int lr = tid >> 3, lc = tid & 7;
+        auto issue = [&](int kb) {    // cp.async of k-block kb into stage kb % kAStages
+            const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
+            const int gk = kb0 + kb * BK + lc * 4;
+            const int kleft = kb1 - gk;
+            const uint32_t kbytes = kleft >= 4 ? 16u : (kleft > 0 ? uint32_t(kleft) * 4u : 0u);
 #pragma unroll
-        for (int u = 0; u < kRa; ++u) {
-            const int r = lr + kRows * u, gr = m0 + r;
-            const bool ok = gr < g.M && kbytes > 0;
-            cp_async16(st + sw128_off(r, lc), ok ? static_cast<const void*>(g.A + size_t(gr) * g.lda + gk) : static_cast<const void*>(g.A),
-                       ok ? kbytes : 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < kRb; ++u) {
-            const int r = lr + kRows * u, gr = n0 + r;
-            const bool ok = gr < g.N && kbytes > 0;
-            cp_async16(st + SL::kATile + sw128_off(r, lc),
-                       ok ? static_cast<const void*>(g.B + size_t(gr) * g.ldb + gk) : static_cast<const void*>(g.B), ok ? kbytes : 0u);
-        }
-    };
-    // prologue: two k-blocks in flight
-    for (int j = 0; j < 2; ++j) {
-        if (j < n_kb) issue(j);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    for (int kb = 0; kb < n_kb; ++kb) {
-        // MMAs of k-block kb - 2 done => raw stage (kb + 2) % kAStages and lo buffer kb % 2 are free again
-        if (kb >= 2) mbar_wait(&s_bar[(kb - 2) % kAStages], uint32_t(((kb - 2) / kAStages) & 1));
-        if (kb + 2 < n_kb) issue(kb + 2);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's chunks of k-block kb have landed
-        const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
-        const uint32_t lo = lo_base + (kb & 1) * SL::kStageBytes;
-        if (PASSES == 3) {
-#pragma unroll
-            for (int u = 0; u < kRa + kRb; ++u) {
-                const uint32_t off = (u < kRa ? 0u : uint32_t(SL::kATile)) + sw128_off(lr + kRows * (u < kRa ? u : u - kRa), lc);
-                float4 v;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(v.x - h.x), "f"(v.y - h.y), "f"(v.z - h.z),
-                             "f"(v.w - h.w)
-                             : "memory");
+            for (int u = 0; u < kRa; ++u) {
+                const int r = lr + kRows * u, gr = m0 + r;
+                const bool ok = gr < g.M && kbytes > 0;
+                cp_async16(st + sw128_off(r, lc), ok ? static_cast<const void*>(g.A + size_t(gr) * g.lda + gk) : static_cast<const void*>(g.A),
+                           ok ? kbytes : 0u);
             }
+#pragma unroll
+            for (int u = 0; u < kRb; ++u) {
+                const int r = lr + kRows * u, gr = n0 + r;
+                const bool ok = gr < g.N && kbytes > 0;
+                cp_async16(st + SL::kATile + sw128_off(r, lc),
+                           ok ? static_cast<const void*>(g.B + size_t(gr) * g.ldb + gk) : static_cast<const void*>(g.B), ok ? kbytes : 0u);
+            }
+        };
+        for (int j = 0; j < 2; ++j) {            // prologue: two k-blocks in flight
+            if (j < n_kb) issue(j);
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
+        for (int kb = 0; kb < n_kb; ++kb) {
+            // MMAs of k-block kb - 2 done => raw stage (kb + 2) % kAStages and lo buffer kb % 2 are free again
+            if (kb >= 2) mbar_wait(&s_free[(kb - 2) % kAStages], uint32_t(((kb - 2) / kAStages) & 1));
+            if (kb + 2 < n_kb) issue(kb + 2);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's chunks of k-block kb have landed
+            const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
+            const uint32_t lo = lo_base + (kb & 1) * SL::kStageBytes;
+            if (PASSES == 3) {
+#pragma unroll
+                for (int u = 0; u < kRa + kRb; ++u) {
+                    const uint32_t off = (u < kRa ? 0u : uint32_t(SL::kATile)) + sw128_off(lr + kRows * (u < kRa ? u : u - kRa), lc);
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(v.x - h.x), "f"(v.y - h.y), "f"(v.z - h.z),
+                                 "f"(v.w - h.w)
+                                 : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy writes -> visible to the tensor core
+            mbar_arrive(&s_full[kb % kAStages]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (tid == kProducerThreads) {
+        // ------------------------------------------------ MMA issuer -----------------------------------------------
+        for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(&s_full[kb % kAStages], uint32_t((kb / kAStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
+            const uint32_t lo = lo_base + (kb & 1) * SL::kStageBytes;
             const uint64_t da_hi = make_desc_k_sw128(st), db_hi = make_desc_k_sw128(st + SL::kATile);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
@@ -403,17 +423,18 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
                     umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, acc0);
                 }
             }
-            umma_commit(&s_bar[kb % kAStages]);
+            umma_commit(&s_free[kb % kAStages]);   // arrives when every MMA issued so far has completed
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (n_kb > 0) {
-        const int last = n_kb - 1;
-        mbar_wait(&s_bar[last % kAStages], uint32_t((last / kAStages) & 1));
+    if (warp < kProducerThreads / 32) {
+        if (n_kb > 0) {
+            const int last = n_kb - 1;
+            mbar_wait(&s_free[last % kAStages], uint32_t((last / kAStages) & 1));   // the last commit covers the whole tile
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // two warpgroups split the columns: warps 0-3 take [0, BN/2), warps 4-7 take [BN/2, BN)
+        tc_epilogue<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0);
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // two warpgroups split the columns: warps 0-3 take [0, BN/2), warps 4-7 take [BN/2, BN)
-    tc_epilogue<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
