@@ -24,14 +24,13 @@ namespace szb {
 // ---- constant tables (uploaded per device at context creation) ------------------------------------------------------
 __constant__ float2 c_tw400[kR * kR];     // W_400^{n1 k2}
 __constant__ float2 c_tw800[201];         // W_800^k, k = 0..200
-__constant__ float c_melw[768];           // non-zero mel weights, pre-scaled by 1 / (4 * 32767^2)
-__constant__ int c_mel_start[kMels];
-__constant__ int c_mel_len[kMels];
-__constant__ int c_mel_off[kMels];
+constexpr int kMelPad = 8;                // mel chunks are zero-padded to multiples of 8 bins (unrolled inner loop)
+constexpr int kMelWCap = 48 * 40;         // capacity of the padded weight table
+__constant__ float c_melw[kMelWCap];      // per-task mel weights, pre-scaled by 1 / (4 * 32767^2), zero-padded
 __constant__ float c_dct[kMfcc * kMels];  // unscaled DCT-II rows
 // The 26 filters hold 3..105 non-zero bins each; they are cut into chunks of <= 40 bins ("tasks") that are spread
 // over the 20 warps by size (longest-processing-time first) so the mel stage ends at the same time on every warp.
-struct MelTask { short k0, len, woff, slot; };
+struct MelTask { short k0, len, woff, slot; };   // len is a multiple of kMelPad
 constexpr int kMaxMelTasks = 48;
 __constant__ MelTask c_mel_tasks[kMaxMelTasks];      // grouped by warp
 __constant__ int c_mel_warp_begin[20 + 1];           // tasks of warp w: [begin[w], begin[w+1])
@@ -47,20 +46,21 @@ constexpr int kRing = 64;                 // MFCC ring slots (power of two >= kT
 
 constexpr size_t kSmemPcm = size_t(kPcmRows) * kHopStride * 4;          // 26 532
 constexpr size_t kSmemS = size_t(kHalf) * kTile * 8;                    // 102 400
-constexpr size_t kSmemP = size_t(kBins) * kTile * 4;                    // 51 328
+constexpr size_t kSmemP = size_t(kBins + kMelPad) * kTile * 4;          // 52 352: power rows + zero rows read by padded mel taps
 constexpr size_t kSmemE = size_t(kMels + kMaxMelTasks) * kTile * 4;     // 9 472: ln energies + partial sums
-constexpr size_t kSmemRing = size_t(kMfcc) * kRing * 4;                 // 5 120
-constexpr size_t kSmemRed = size_t(2 * kWarps) * 32 * 4;                // 5 120: per-warp sum and sum of squares
-constexpr size_t kSmemOut = size_t(kTile) * kFeat * 4;                  // 7 680
+constexpr int kRingStride = kRing + 1;                                  // 65: lane = coefficient reads stay conflict-free
+constexpr size_t kSmemRing = size_t(kMfcc) * kRingStride * 4;           // 5 200
+// The mel weights (7.7 KB, each read once per tile) do not fit the indexed-constant cache next to the twiddles and the
+// DCT rows; they are copied into shared memory once per CTA (a warp-uniform LDS is a single-wavefront broadcast).
+constexpr size_t kSmemMelW = size_t(kMelWCap) * 4;                      // 7 680
 constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 constexpr size_t kOffPcm = 0;
 constexpr size_t kOffS = align16(kOffPcm + kSmemPcm);
 constexpr size_t kOffP = align16(kOffS + kSmemS);
 constexpr size_t kOffE = align16(kOffP + kSmemP);
 constexpr size_t kOffRing = align16(kOffE + kSmemE);
-constexpr size_t kOffRed = align16(kOffRing + kSmemRing);
-constexpr size_t kOffOut = align16(kOffRed + kSmemRed);
-constexpr size_t kSmemTotal = align16(kOffOut + kSmemOut);
+constexpr size_t kOffMelW = align16(kOffRing + kSmemRing);
+constexpr size_t kSmemTotal = align16(kOffMelW + kSmemMelW);
 static_assert(kSmemTotal <= 227 * 1024, "front-end tile does not fit in shared memory");
 
 // (x[2n], x[2n+1]) packed in one word -> two floats; cvt.rn.f32.s16 reads the 16-bit halves directly
@@ -78,11 +78,13 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
     float* s_P = reinterpret_cast<float*>(smem + kOffP);
     float* s_E = reinterpret_cast<float*>(smem + kOffE);
     float* s_ring = reinterpret_cast<float*>(smem + kOffRing);
-    float* s_red = reinterpret_cast<float*>(smem + kOffRed);
-    float* s_out = reinterpret_cast<float*>(smem + kOffOut);
+    float* s_melw = reinterpret_cast<float*>(smem + kOffMelW);
     __shared__ uint32_t s_seg;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kMelPad * kTile; i += kThreads) s_P[kBins * kTile + i] = 0.f;   // rows 401.. stay zero
+    for (int i = tid; i < kMelWCap; i += kThreads) s_melw[i] = c_melw[i];
+    __syncthreads();
 
     for (;;) {
         if (tid == 0) s_seg = atomicAdd(queue, 1u);
@@ -218,19 +220,17 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             // ---- 5a. mel partial sums: size-balanced chunks of the sparse 26 x 401 bank (lib.rs:303-308) ----------------
             for (int t = c_mel_warp_begin[warp]; t < c_mel_warp_begin[warp + 1]; ++t) {
                 const MelTask mt = c_mel_tasks[t];
-                const float* wv = c_melw + mt.woff;
+                const float* wv = s_melw + mt.woff;
                 const float* pp = s_P + mt.k0 * kTile + lane;
                 float acc0 = 0.f, acc1 = 0.f;
-                int i = 0;
 #pragma unroll 1
-                for (; i + 8 <= mt.len; i += 8) {
+                for (int i = 0; i < mt.len; i += kMelPad) {
 #pragma unroll
-                    for (int u = 0; u < 8; u += 2) {
+                    for (int u = 0; u < kMelPad; u += 2) {
                         acc0 = fmaf(wv[i + u], pp[(i + u) * kTile], acc0);
                         acc1 = fmaf(wv[i + u + 1], pp[(i + u + 1) * kTile], acc1);
                     }
                 }
-                for (; i < mt.len; ++i) acc0 = fmaf(wv[i], pp[i * kTile], acc0);
                 s_E[(kMels + mt.slot) * kTile + lane] = acc0 + acc1;
             }
             __syncthreads();
@@ -242,10 +242,9 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             }
             __syncthreads();
 
-            // ---- 6. DCT-II, first 20 coefficients: warp = coefficient j, lane = frame (lib.rs:312-315).  Row j of the MFCC
-            //         ring is written and read by warp j only, so the delta stage below needs no block barrier. ------------
-            const int j = warp;
+            // ---- 6. DCT-II, first 20 coefficients: warp = coefficient j, lane = frame (lib.rs:312-315) ----------------
             {
+                const int j = warp;
                 const float* dj = c_dct + j * kMels;
                 float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
@@ -253,20 +252,22 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                     acc0 = fmaf(dj[m], s_E[m * kTile + lane], acc0);
                     acc1 = fmaf(dj[m + 1], s_E[(m + 1) * kTile + lane], acc1);
                 }
-                if (uint32_t(lane) < nf) s_ring[j * kRing + ((a + lane) & (kRing - 1))] = acc0 + acc1;
+                if (uint32_t(lane) < nf) s_ring[j * kRingStride + ((a + lane) & (kRing - 1))] = acc0 + acc1;
             }
-            __syncwarp();
+            __syncthreads();
 
-            // ---- 7. delta, delta-delta, z-score and store for the windows whose +-2 neighbours are now known ----------
+            // ---- 7. delta, delta-delta, z-score and store for the windows whose +-2 neighbours are now known.
+            //         warp = window, lane = coefficient j (< 20): the 60-value mean / variance is a warp shuffle
+            //         reduction, the three 20-float thirds of the row are stored straight to global memory (80
+            //         contiguous bytes per store) -- no further block barrier, no shared staging. ----------------------
             const bool last = a + nf >= f_hi;
             const uint32_t lim = last ? sg.w_end : min(sg.w_end, a + nf - 2);
-            for (uint32_t w0 = emit_next; w0 < lim; w0 += kTile) {
-                const uint32_t w = w0 + lane;
-                const bool valid = w < lim;
+            for (uint32_t w = emit_next + warp; w < lim; w += kWarps) {
+                const int j = lane;
                 float c0 = 0.f, d1 = 0.f, d2 = 0.f;
-                if (valid) {
+                if (j < kMfcc) {
                     const int hi = int(n_total) - 1;
-                    const float* rj = s_ring + j * kRing;
+                    const float* rj = s_ring + j * kRingStride;
                     auto cl = [hi](int x) { return min(max(x, 0), hi); };
                     auto C = [rj](int g) { return rj[g & (kRing - 1)]; };
                     const int ip = cl(int(w) + 1), im = cl(int(w) - 1);
@@ -276,30 +277,21 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                     const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;       // delta at clamp(w-1)
                     d2 = (dp - dm) * 0.5f;                                         // lib.rs:322
                 }
-                // per-window sums over the 60 values: each warp contributes its coefficient's three entries
-                s_red[warp * 32 + lane] = c0 + d1 + d2;
-                s_red[(kWarps + warp) * 32 + lane] = fmaf(c0, c0, fmaf(d1, d1, d2 * d2));
-                __syncthreads();
-                float sum = 0.f, sq = 0.f;
+                float sum = c0 + d1 + d2;
 #pragma unroll
-                for (int q = 0; q < kWarps; ++q) {
-                    sum += s_red[q * 32 + lane];
-                    sq += s_red[(kWarps + q) * 32 + lane];
-                }
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const float mean = sum / float(kFeat);                             // lib.rs:328
-                // population variance (lib.rs:329-336) as E[v^2] - mean^2: one reduction instead of two; the 60 values
-                // span |c0| >> |mean|, so there is no cancellation (error ~1e-6 relative, tests hold 1e-4 absolute)
-                const float var = fmaxf(sq / float(kFeat) - mean * mean, 0.f);
-                const float sd = fmaxf(sqrtf(var), 1e-6f);                         // lib.rs:337
-                s_out[lane * kFeat + j] = (c0 - mean) / sd;                        // lib.rs:338-340
-                s_out[lane * kFeat + kMfcc + j] = (d1 - mean) / sd;
-                s_out[lane * kFeat + 2 * kMfcc + j] = (d2 - mean) / sd;
-                __syncthreads();
-                const uint32_t nvalid = min(uint32_t(kTile), lim - w0);
-                float4* dst = reinterpret_cast<float4*>(out_clip + size_t(w0) * kFeat);
-                const float4* srcv = reinterpret_cast<const float4*>(s_out);
-                for (uint32_t i = tid; i < nvalid * (kFeat / 4); i += kThreads) dst[i] = srcv[i];
-                if (w0 + kTile < lim) __syncthreads();   // a second chunk (clip end only) reuses s_red / s_out
+                const float e0 = c0 - mean, e1 = d1 - mean, e2 = d2 - mean;
+                float sq = j < kMfcc ? fmaf(e0, e0, fmaf(e1, e1, e2 * e2)) : 0.f;   // two-pass variance, lib.rs:329-336
+#pragma unroll
+                for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                const float sd = fmaxf(sqrtf(sq / float(kFeat)), 1e-6f);           // lib.rs:337
+                if (j < kMfcc) {
+                    float* row = out_clip + size_t(w) * kFeat;
+                    row[j] = e0 / sd;                                              // lib.rs:338-340
+                    row[kMfcc + j] = e1 / sd;
+                    row[2 * kMfcc + j] = e2 / sd;
+                }
             }
             emit_next = max(emit_next, lim);
         }
@@ -436,20 +428,14 @@ szb_status upload_frontend_tables() {
     const auto dense = mel_filterbank_dense();
     const MelCsr csr = mel_filterbank_csr(dense);
     const auto dct = dct2_rows();
-    SZB_REQUIRE(csr.w.size() <= 768, "mel bank has %zu non-zeros, table holds 768", csr.w.size());
-    std::vector<float> melw(768, 0.f);
     const double scale = 1.0 / (4.0 * 32767.0 * 32767.0);  // undo integer-valued input and the unscaled real split
-    for (size_t i = 0; i < csr.w.size(); ++i) melw[i] = float(double(csr.w[i]) * scale);
     SZB_CUDA(cudaMemcpyToSymbol(c_tw400, tw400.data(), tw400.size() * sizeof(float)));
     SZB_CUDA(cudaMemcpyToSymbol(c_tw800, tw800.data(), tw800.size() * sizeof(float)));
-    SZB_CUDA(cudaMemcpyToSymbol(c_melw, melw.data(), melw.size() * sizeof(float)));
-    SZB_CUDA(cudaMemcpyToSymbol(c_mel_start, csr.start, sizeof(csr.start)));
-    SZB_CUDA(cudaMemcpyToSymbol(c_mel_len, csr.len, sizeof(csr.len)));
-    SZB_CUDA(cudaMemcpyToSymbol(c_mel_off, csr.off, sizeof(int) * kMels));
     SZB_CUDA(cudaMemcpyToSymbol(c_dct, dct.data(), dct.size() * sizeof(float)));
     {   // mel tasks: chunks of <= 40 bins, longest-processing-time-first over the warps
         struct T { MelTask t; int m; };
         std::vector<T> tasks;
+        std::vector<float> melw;
         int part_begin[kMels + 1];
         int slot = 0;
         for (int m = 0; m < kMels; ++m) {
@@ -457,8 +443,13 @@ szb_status upload_frontend_tables() {
             const int len = csr.len[m], parts = std::max(1, (len + 39) / 40);
             for (int p = 0; p < parts; ++p) {
                 const int b = len * p / parts, e = len * (p + 1) / parts;
+                const int padded = (e - b + kMelPad - 1) / kMelPad * kMelPad;   // extra taps are exact zeros
+                SZB_REQUIRE(melw.size() + size_t(padded) <= size_t(kMelWCap), "mel weight table overflow");
                 MelTask t;
-                t.k0 = short(csr.start[m] + b); t.len = short(e - b); t.woff = short(csr.off[m] + b); t.slot = short(slot++);
+                t.k0 = short(csr.start[m] + b); t.len = short(padded); t.woff = short(melw.size()); t.slot = short(slot++);
+                for (int i = 0; i < padded; ++i)
+                    melw.push_back(i < e - b ? float(double(csr.w[size_t(csr.off[m]) + b + i]) * scale) : 0.f);
+                SZB_REQUIRE(t.k0 + padded <= kBins + kMelPad, "padded mel chunk runs past the zero rows");
                 tasks.push_back({ t, m });
             }
         }
@@ -480,6 +471,8 @@ szb_status upload_frontend_tables() {
             for (const MelTask& t : per_warp[w]) flat[n++] = t;
         }
         warp_begin[kWarps] = n;
+        melw.resize(kMelWCap, 0.f);
+        SZB_CUDA(cudaMemcpyToSymbol(c_melw, melw.data(), melw.size() * sizeof(float)));
         SZB_CUDA(cudaMemcpyToSymbol(c_mel_tasks, flat, sizeof flat));
         SZB_CUDA(cudaMemcpyToSymbol(c_mel_warp_begin, warp_begin, sizeof warp_begin));
         SZB_CUDA(cudaMemcpyToSymbol(c_mel_part_begin, part_begin, sizeof part_begin));
