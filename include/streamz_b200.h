@@ -187,6 +187,20 @@ szb_status szb_identify_sums(szb_net* net, const float* feats, uint64_t n_window
 szb_status szb_identify_speaker_list(szb_net* net, const int16_t* pcm, uint64_t n_samples, float threshold,
                                      uint32_t* speakers, uint32_t cap, uint32_t* n_speakers);
 
+/* ---- embeddings (SURVEY.md 8(f) "next" row N1; lib.rs:893-905, 1073-1079, 1413-1540) -------------------------------- */
+/* embedding_size (lib.rs:903) */
+szb_status szb_net_embedding_size(const szb_net* net, uint32_t* size);
+/* Second hidden layer for B windows, out [B][h2]: relu2 = 0 is `embed` (ReLU, tanh; lib.rs:895-900), relu2 = 1 is
+ * `forward_embedding` (ReLU, ReLU; lib.rs:1073-1079). */
+szb_status szb_net_embed(szb_net* net, const float* x, uint64_t B, int32_t relu2, float* out);
+/* extract_embedding_from_features (lib.rs:1453-1475): mean of forward_embedding over the windows, L2-normalised. */
+szb_status szb_net_embedding_mean(szb_net* net, const float* feats, uint64_t n_windows, float* out /* [h2] */);
+/* Per-dimension median over the windows, L2-normalised: relu2 = 1 is median_embedding_from_features (lib.rs:1478-1500),
+ * relu2 = 0 the reduction of extract_embedding (lib.rs:1418-1450).  No windows: zero vector. */
+szb_status szb_net_embedding_median(szb_net* net, const float* feats, uint64_t n_windows, int32_t relu2, float* out);
+/* cosine_similarity (lib.rs:1531-1540) */
+float szb_cosine_similarity(const float* a, const float* b, uint32_t n);
+
 /* ---- multi-GPU: batch-parallel training, one NCCL all-reduce of the flattened gradient per step --------------------- */
 szb_status szb_comm_unique_id(uint8_t id[128]);
 szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);

@@ -298,6 +298,50 @@ inline std::vector<size_t> identify_speaker_list(const SimpleNeuralNet& net, con
     return std::vector<size_t>(out.begin(), out.begin() + n);
 }
 
+// ---- embeddings and cosine matching (lib.rs:893-905, 1073-1079, 1413-1540) -------------------------------------------
+inline std::vector<float> embed(const SimpleNeuralNet& net, const std::vector<float>& bits) {   // lib.rs:895
+    uint32_t h2 = 0;
+    check(szb_net_embedding_size(net.handle(), &h2));
+    std::vector<float> out(h2);
+    check(szb_net_embed(net.handle(), bits.data(), 1, 0, out.data()));
+    return out;
+}
+inline std::vector<float> forward_embedding(const SimpleNeuralNet& net, const std::vector<float>& input) {   // lib.rs:1073
+    uint32_t h2 = 0;
+    check(szb_net_embedding_size(net.handle(), &h2));
+    std::vector<float> out(h2);
+    check(szb_net_embed(net.handle(), input.data(), 1, 1, out.data()));
+    return out;
+}
+inline std::vector<float> extract_embedding_from_features(const SimpleNeuralNet& net, const Windows& feats) {   // lib.rs:1453
+    uint32_t h2 = 0;
+    check(szb_net_embedding_size(net.handle(), &h2));
+    std::vector<float> out(h2);
+    const std::vector<float> flat = detail::flatten(feats, net.input_size());
+    check(szb_net_embedding_mean(net.handle(), flat.data(), feats.size(), out.data()));
+    return out;
+}
+inline std::vector<float> median_embedding_from_features(const SimpleNeuralNet& net, const Windows& feats) {   // lib.rs:1478
+    uint32_t h2 = 0;
+    check(szb_net_embedding_size(net.handle(), &h2));
+    std::vector<float> out(h2);
+    const std::vector<float> flat = detail::flatten(feats, net.input_size());
+    check(szb_net_embedding_median(net.handle(), flat.data(), feats.size(), 1, out.data()));
+    return out;
+}
+inline std::vector<float> extract_embedding(const SimpleNeuralNet& net, const std::vector<int16_t>& sample, const FeatureExtractor& extractor) {   // lib.rs:1418
+    uint32_t h2 = 0;
+    check(szb_net_embedding_size(net.handle(), &h2));
+    std::vector<float> out(h2);
+    const Windows w = extractor.extract(sample);
+    const std::vector<float> flat = detail::flatten(w, net.input_size());
+    check(szb_net_embedding_median(net.handle(), flat.data(), w.size(), 0, out.data()));
+    return out;
+}
+inline float cosine_similarity(const std::vector<float>& a, const std::vector<float>& b) {   // lib.rs:1531
+    return szb_cosine_similarity(a.data(), b.data(), uint32_t(std::min(a.size(), b.size())));
+}
+
 // lib.rs:558-579; decoding stays on the host and is out of scope, so the caller passes the decoded mono 44.1 kHz samples.
 inline Windows load_cached_features(const std::string& path, const std::function<std::vector<int16_t>(const std::string&)>& load_audio_samples,
                                     const FeatureExtractor& extractor) {

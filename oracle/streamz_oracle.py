@@ -494,6 +494,70 @@ def identify_speaker_with_threshold_feats(net: Net, feats: np.ndarray, threshold
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# Embeddings and cosine matching (lib.rs:131-139, 1413-1661)
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def normalize(v: np.ndarray) -> np.ndarray:
+    """lib.rs:132-139: divide by the L2 norm when it exceeds 1e-6."""
+    v = np.asarray(v).copy()
+    norm = np.sqrt((v * v).sum(dtype=v.dtype))
+    return v / norm if norm > 1e-6 else v
+
+
+def embedding_mean(net: Net, feats: np.ndarray) -> np.ndarray:
+    """extract_embedding_from_features (lib.rs:1453-1475)."""
+    if feats.shape[0] == 0:
+        return np.zeros(net.w2.shape[1], dtype=net.dtype)
+    e = forward_embedding(net, feats)
+    return normalize(e.sum(axis=0, dtype=net.dtype) / net.dtype(feats.shape[0]))
+
+
+def embedding_median(net: Net, feats: np.ndarray, relu2: bool = True) -> np.ndarray:
+    """median_embedding_from_features (relu2, lib.rs:1478-1500) / the reduction of extract_embedding (lib.rs:1418-1450):
+    per-dimension median (mean of the two middle values for an even count), then normalize."""
+    if feats.shape[0] == 0:
+        return np.zeros(net.w2.shape[1], dtype=net.dtype)
+    e = forward_embedding(net, feats) if relu2 else embed(net, feats)
+    srt = np.sort(e, axis=0)
+    n = e.shape[0]
+    med = srt[n // 2] if n % 2 else (srt[n // 2 - 1] + srt[n // 2]) / net.dtype(2.0)
+    return normalize(med.astype(net.dtype))
+
+
+def cosine_similarity(a: np.ndarray, b: np.ndarray) -> float:
+    """lib.rs:1531-1540."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    na, nb = np.sqrt((a * a).sum()), np.sqrt((b * b).sum())
+    return 0.0 if na == 0 or nb == 0 else float((a * b).sum() / (na * nb))
+
+
+def identify_speaker_from_embedding(emb, speaker_embeddings: dict, threshold: float):
+    """lib.rs:1503-1529: best cosine match; threshold relaxed by 0.7 with fewer than 20 speakers; None for usize::MAX."""
+    best_sim, best_id = -np.inf, None
+    for sid, centroid in speaker_embeddings.items():
+        sim = cosine_similarity(emb, centroid)
+        if sim > best_sim:
+            best_sim, best_id = sim, sid
+    dyn = threshold * 0.7 if len(speaker_embeddings) < 20 else threshold
+    return best_id if best_sim > dyn else None
+
+
+def identify_speaker_cosine_emb(emb, speaker_embeds, threshold: float):
+    """Decision rule shared by identify_speaker_cosine / _feats (lib.rs:1604-1661); speaker_embeds = [(mean, mean_sim, std_sim)]."""
+    best_idx, best_val = None, threshold
+    for i, (mean, mean_sim, std_sim) in enumerate(speaker_embeds):
+        sim = cosine_similarity(emb, mean)
+        if sim < mean_sim - 2.0 * std_sim:
+            continue
+        factor = 0.3 if len(speaker_embeds) < 200 else 1.0
+        dyn = mean_sim + std_sim * factor
+        if sim > 0.35 and (sim > dyn or sim > 0.5) and sim > best_val:
+            best_val, best_idx = sim, i
+    return best_idx
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # Synthetic audio (SURVEY.md section 8(d) generator; deterministic)
 # ----------------------------------------------------------------------------------------------------------------------
 

@@ -87,6 +87,11 @@ SIGNATURES = {
     "szb_identify_counts_dev": (i32, [vp, vp, u64, f32, vp]),
     "szb_identify_sums": (i32, [vp, vp, u64, vp]),
     "szb_identify_speaker_list": (i32, [vp, vp, u64, f32, vp, u32, P(u32)]),
+    "szb_net_embedding_size": (i32, [vp, P(u32)]),
+    "szb_net_embed": (i32, [vp, vp, u64, i32, vp]),
+    "szb_net_embedding_mean": (i32, [vp, vp, u64, vp]),
+    "szb_net_embedding_median": (i32, [vp, vp, u64, i32, vp]),
+    "szb_cosine_similarity": (f32, [vp, vp, u32]),
     "szb_comm_unique_id": (i32, [vp]),
     "szb_comm_init": (i32, [vp, vp, i32, i32]),
     "szb_comm_destroy": (i32, [vp]),

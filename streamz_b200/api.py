@@ -488,6 +488,108 @@ def identify_speaker_list(net: SimpleNeuralNet, sample, threshold: float, extrac
     return [int(x) for x in out[: n.value]]
 
 
+# ---- embeddings and cosine matching ----------------------------------------------------------------
+
+def embedding_size(net: SimpleNeuralNet) -> int:
+    n = C.c_uint32()
+    N.check(N.lib.szb_net_embedding_size(net._h, C.byref(n)))
+    return int(n.value)
+
+
+def embed(net: SimpleNeuralNet, x, relu2: bool = False) -> np.ndarray:
+    """``embed`` (ReLU, tanh; lib.rs:895-900) or, with ``relu2``, ``forward_embedding`` (ReLU, ReLU; lib.rs:1073-1079)."""
+    x = _f32(x)
+    single = x.ndim == 1
+    x2 = x.reshape(1, -1) if single else x
+    out = np.empty((x2.shape[0], embedding_size(net)), dtype=np.float32)
+    N.check(N.lib.szb_net_embed(net._h, N.ptr(x2), x2.shape[0], 1 if relu2 else 0, N.ptr(out)))
+    return out[0] if single else out
+
+
+def forward_embedding(net: SimpleNeuralNet, x) -> np.ndarray:
+    return embed(net, x, relu2=True)
+
+
+def extract_embedding_from_features(net: SimpleNeuralNet, feats) -> np.ndarray:
+    """lib.rs:1453-1475."""
+    w = _f32(feats).reshape(-1, net.dims[0])
+    out = np.empty(embedding_size(net), dtype=np.float32)
+    N.check(N.lib.szb_net_embedding_mean(net._h, N.ptr(w), w.shape[0], N.ptr(out)))
+    return out
+
+
+def median_embedding_from_features(net: SimpleNeuralNet, feats, relu2: bool = True) -> np.ndarray:
+    """lib.rs:1478-1500."""
+    w = _f32(feats).reshape(-1, net.dims[0])
+    out = np.empty(embedding_size(net), dtype=np.float32)
+    N.check(N.lib.szb_net_embedding_median(net._h, N.ptr(w), w.shape[0], 1 if relu2 else 0, N.ptr(out)))
+    return out
+
+
+def extract_embedding(net: SimpleNeuralNet, sample, extractor: FeatureExtractor) -> np.ndarray:
+    """lib.rs:1418-1450: per-dimension median of ``embed`` over the clip's windows, normalised."""
+    return median_embedding_from_features(net, extractor.extract(sample), relu2=False)
+
+
+def cosine_similarity(a, b) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(N.lib.szb_cosine_similarity(N.ptr(a), N.ptr(b), len(a)))
+
+
+def identify_speaker_from_embedding(emb, speaker_embeddings: Dict[int, np.ndarray], threshold: float) -> Optional[int]:
+    """lib.rs:1503-1529 (``None`` stands for ``usize::MAX``)."""
+    best_sim, best_id = -np.inf, None
+    for sid, centroid in speaker_embeddings.items():
+        sim = cosine_similarity(emb, centroid)
+        if sim > best_sim:
+            best_sim, best_id = sim, sid
+    dyn = threshold * 0.7 if len(speaker_embeddings) < 20 else threshold
+    return best_id if best_sim > dyn else None
+
+
+def _cosine_decision(emb, speaker_embeds, threshold: float) -> Optional[int]:
+    best_idx, best_val = None, threshold
+    for i, (mean, mean_sim, std_sim) in enumerate(speaker_embeds):
+        sim = cosine_similarity(emb, mean)
+        if sim < mean_sim - 2.0 * std_sim:
+            continue
+        factor = 0.3 if len(speaker_embeds) < 200 else 1.0
+        if sim > 0.35 and (sim > mean_sim + std_sim * factor or sim > 0.5) and sim > best_val:
+            best_val, best_idx = sim, i
+    return best_idx
+
+
+def identify_speaker_cosine_feats(net: SimpleNeuralNet, speaker_embeds, windows, threshold: float) -> Optional[int]:
+    """lib.rs:1635-1661."""
+    if not speaker_embeds:
+        return None
+    return _cosine_decision(extract_embedding_from_features(net, windows), speaker_embeds, threshold)
+
+
+def identify_speaker_cosine(net: SimpleNeuralNet, speaker_embeds, sample, threshold: float, extractor: FeatureExtractor) -> Optional[int]:
+    """lib.rs:1604-1632."""
+    if not speaker_embeds:
+        return None
+    return _cosine_decision(extract_embedding(net, sample, extractor), speaker_embeds, threshold)
+
+
+def compute_speaker_embeddings(net: SimpleNeuralNet, features_by_path: Dict[str, np.ndarray]):
+    """lib.rs:1555-1599: per speaker (mean of the files' median embeddings, mean cosine to it, std of the cosines)."""
+    out = []
+    h2 = embedding_size(net)
+    for files in net.file_lists():
+        embeds = [median_embedding_from_features(net, features_by_path[p]) for p in files if p in features_by_path]
+        if not embeds:
+            out.append((np.zeros(h2, np.float32), 0.0, 0.0))
+            continue
+        mean = np.mean(np.stack(embeds), axis=0, dtype=np.float32)
+        norm = np.sqrt((mean * mean).sum())
+        mean = mean / norm if norm > 1e-6 else mean
+        sims = np.array([cosine_similarity(e, mean) for e in embeds], np.float32)
+        out.append((mean.astype(np.float32), float(sims.mean()), float(np.sqrt(((sims - sims.mean()) ** 2).mean()))))
+    return out
+
+
 def feature_cache_path(path: str) -> str:
     """lib.rs:550-555 (does not create the directory)."""
     buf = C.create_string_buffer(len(path) + 64)

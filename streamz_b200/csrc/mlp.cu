@@ -6,6 +6,7 @@
 // (bias+ReLU, bias+tanh, bias, *tanh', *ReLU').  Results follow the reference's arithmetic in FP32 exactly up to
 // summation order.  See DESIGN.md "MLP kernels".
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -237,6 +238,69 @@ __global__ void init_uniform_kernel(float* __restrict__ w, size_t n, unsigned lo
     }
 }
 
+
+// ---- embeddings (embed lib.rs:895-900, forward_embedding lib.rs:1073-1079) --------------------------
+// Exact per-column order statistic of E[n][ld] by 4-pass radix select on order-preserving keys (one CTA per column):
+// out[c] = value of rank r0 (and r1 when r1 != r0, averaged) -- the median of lib.rs:1438-1447 / 1487-1496.
+__device__ __forceinline__ uint32_t f32_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__global__ void column_median_kernel(const float* __restrict__ E, uint32_t n, int ld, float* __restrict__ out) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rank;
+    const int c = blockIdx.x;
+    const uint32_t ranks[2] = { (n % 2 == 0) ? n / 2 - 1 : n / 2, n / 2 };
+    float vals[2];
+    for (int which = 0; which < 2; ++which) {
+        if (which == 1 && ranks[1] == ranks[0]) { vals[1] = vals[0]; break; }
+        if (threadIdx.x == 0) { s_prefix = 0; s_rank = ranks[which]; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t k = f32_key(E[size_t(i) * ld + c]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t r = s_rank, b = 0;
+                for (; b < 256; ++b) {
+                    if (r < hist[b]) break;
+                    r -= hist[b];
+                }
+                s_rank = r;
+                s_prefix = prefix | (b << shift);
+            }
+            __syncthreads();
+        }
+        vals[which] = key_f32(s_prefix);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = (ranks[0] == ranks[1]) ? vals[0] : (vals[0] + vals[1]) / 2.0f;   // lib.rs:1441-1445
+}
+
+// out[c] = sum_r E[r][c] (mean embedding, lib.rs:1455-1462); deterministic: one CTA per 32 columns, fixed order
+__global__ void column_sum_kernel(const float* __restrict__ E, uint32_t n, int cols, int ld, float* __restrict__ out) {
+    __shared__ float part[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < cols)
+        for (uint32_t r = ry; r < n; r += 8) acc += E[size_t(r) * ld + c];
+    part[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float t = 0.f;
+        for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x & 31];
+        out[c] = t;
+    }
+}
+
 szb_status net_reserve_rows(szb_net* net, uint64_t rows) {
     if (rows <= net->cap_rows) return SZB_OK;
     SZB_TRY(net->xb.reserve(rows * net->n_in * 4));
@@ -325,6 +389,33 @@ static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool train
     SZB_TRY((gemm<false, false, EPI_BIAS>(ctx, B, net->n_out, net->h2, net->a_h2.as<float>(), net->h2, P + net->off_w3(),
                                            net->n_out, net->a_z.as<float>(), net->n_out, P + net->off_b3(), nullptr, 0)));
     return SZB_OK;
+}
+
+
+// Second hidden layer for rows in d_x: relu2 == 0 -> tanh (embed), 1 -> ReLU (forward_embedding).  out: [B][h2].
+static szb_status embed_rows(szb_net* net, const float* d_x, int B, int relu2, float* d_out) {
+    szb_ctx* ctx = net->ctx;
+    float* P = net->params.as<float>();
+    const int I = int(net->n_in), H1 = int(net->h1), H2 = int(net->h2);
+    if (net->precision != 0) {
+        SZB_TRY(refresh_wt(net));
+        const float* WT = net->wt.as<float>();
+        tc::GemmArgs g{};
+        g.A = d_x; g.lda = I; g.B = WT + net->off_wt1(); g.ldb = I; g.C = net->a_h1.as<float>(); g.ldc = H1;
+        g.bias = P + net->off_b1(); g.M = B; g.N = H1; g.K = I;
+        SZB_TRY(gemm_tc<tc::TC_BIAS_RELU>(net, g));
+        g = tc::GemmArgs{};
+        g.A = net->a_h1.as<float>(); g.lda = H1; g.B = WT + net->off_wt2(); g.ldb = H1; g.C = d_out; g.ldc = H2;
+        g.bias = P + net->off_b2(); g.M = B; g.N = H2; g.K = H1;
+        return relu2 ? gemm_tc<tc::TC_BIAS_RELU>(net, g) : gemm_tc<tc::TC_BIAS_TANH>(net, g);
+    }
+    SZB_TRY((gemm<false, false, EPI_BIAS_RELU>(ctx, B, H1, I, d_x, I, P + net->off_w1(), H1, net->a_h1.as<float>(), H1, P + net->off_b1(),
+                                                nullptr, 0)));
+    if (relu2)
+        return gemm<false, false, EPI_BIAS_RELU>(ctx, B, H2, H1, net->a_h1.as<float>(), H1, P + net->off_w2(), H2, d_out, H2,
+                                                 P + net->off_b2(), nullptr, 0);
+    return gemm<false, false, EPI_BIAS_TANH>(ctx, B, H2, H1, net->a_h1.as<float>(), H1, P + net->off_w2(), H2, d_out, H2, P + net->off_b2(),
+                                             nullptr, 0);
 }
 
 static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, const uint32_t* labels, const float* target_vec,
@@ -723,6 +814,95 @@ szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t*
         for (uint32_t i = 0; i < n_in; ++i)
             keep[r * n_in + i] = (prob <= 0.f || dropout_keep(key, rows[r], i, prob)) ? 1 : 0;
     return SZB_OK;
+}
+
+
+// ---- embeddings (N1) ---------------------------------------------------------------------------------------------------
+szb_status szb_net_embedding_size(const szb_net* net, uint32_t* size) {
+    SZB_REQUIRE(net && size, "szb_net_embedding_size: NULL argument");
+    *size = net->h2;
+    return SZB_OK;
+}
+
+// stages the rows (host) and leaves the [n][h2] embeddings in net->d_2-sized scratch; returns the device pointer
+static szb_status embed_all(szb_net* net, const float* feats, uint64_t n, int relu2, float** d_emb) {
+    szb_ctx* ctx = net->ctx;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->x.reserve(std::max<uint64_t>(1, n) * net->n_in * 4));
+    SZB_TRY(ctx->probs.reserve(std::max<uint64_t>(1, n) * net->h2 * 4));
+    if (n) SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, feats, n * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) SZB_TRY(net_reserve_rows(net, std::min(n, kChunkRows)));
+    for (uint64_t r0 = 0; r0 < n; r0 += kChunkRows) {
+        const int nb = int(std::min(kChunkRows, n - r0));
+        SZB_TRY(embed_rows(net, ctx->x.as<float>() + r0 * net->n_in, nb, relu2, ctx->probs.as<float>() + r0 * net->h2));
+    }
+    *d_emb = ctx->probs.as<float>();
+    return SZB_OK;
+}
+
+szb_status szb_net_embed(szb_net* net, const float* x, uint64_t B, int32_t relu2, float* out) {
+    SZB_REQUIRE(net && (B == 0 || (x && out)), "szb_net_embed: NULL argument");
+    if (B == 0) return SZB_OK;
+    float* d = nullptr;
+    SZB_TRY(embed_all(net, x, B, relu2, &d));
+    SZB_CUDA(cudaMemcpyAsync(out, d, B * net->h2 * 4, cudaMemcpyDeviceToHost, net->ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    return SZB_OK;
+}
+
+static void l2_normalize(std::vector<float>& v) {   // normalize(), lib.rs:132-139
+    float norm = 0.f;
+    for (float x : v) norm += x * x;
+    norm = std::sqrt(norm);
+    if (norm > 1e-6f)
+        for (float& x : v) x /= norm;
+}
+
+szb_status szb_net_embedding_mean(szb_net* net, const float* feats, uint64_t n, float* out) {
+    SZB_REQUIRE(net && out && (feats || n == 0), "szb_net_embedding_mean: NULL argument");
+    std::vector<float> acc(net->h2, 0.f);
+    if (n > 0) {   // extract_embedding_from_features, lib.rs:1453-1475: forward_embedding (ReLU, ReLU), mean, normalise
+        float* d = nullptr;
+        SZB_TRY(embed_all(net, feats, n, 1, &d));
+        szb_ctx* ctx = net->ctx;
+        SZB_TRY(net->hist.reserve(size_t(net->h2) * 4));
+        column_sum_kernel<<<(net->h2 + 31) / 32, 256, 0, ctx->stream>>>(d, uint32_t(n), int(net->h2), int(net->h2), net->hist.as<float>());
+        SZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        SZB_CUDA(cudaMemcpyAsync(acc.data(), net->hist.ptr, size_t(net->h2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (float& v : acc) v /= float(n);
+    }
+    l2_normalize(acc);
+    std::memcpy(out, acc.data(), acc.size() * 4);
+    return SZB_OK;
+}
+
+szb_status szb_net_embedding_median(szb_net* net, const float* feats, uint64_t n, int32_t relu2, float* out) {
+    SZB_REQUIRE(net && out && (feats || n == 0), "szb_net_embedding_median: NULL argument");
+    SZB_REQUIRE(n <= 0xffffffffull, "szb_net_embedding_median: too many windows");
+    std::vector<float> emb(net->h2, 0.f);
+    if (n > 0) {   // median_embedding_from_features (relu2 = 1, lib.rs:1478-1500) / extract_embedding (relu2 = 0, lib.rs:1418-1450)
+        float* d = nullptr;
+        SZB_TRY(embed_all(net, feats, n, relu2, &d));
+        szb_ctx* ctx = net->ctx;
+        SZB_TRY(net->hist.reserve(size_t(net->h2) * 4));
+        column_median_kernel<<<net->h2, 256, 0, ctx->stream>>>(d, uint32_t(n), int(net->h2), net->hist.as<float>());
+        SZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        SZB_CUDA(cudaMemcpyAsync(emb.data(), net->hist.ptr, size_t(net->h2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+        l2_normalize(emb);
+    }
+    std::memcpy(out, emb.data(), emb.size() * 4);   // no windows: zero vector, not normalised (lib.rs:1429-1431)
+    return SZB_OK;
+}
+
+float szb_cosine_similarity(const float* a, const float* b, uint32_t n) {   // lib.rs:1531-1540
+    float dot = 0.f, na = 0.f, nb = 0.f;
+    for (uint32_t i = 0; i < n; ++i) { dot += a[i] * b[i]; na += a[i] * a[i]; nb += b[i] * b[i]; }
+    na = std::sqrt(na); nb = std::sqrt(nb);
+    return (na == 0.f || nb == 0.f) ? 0.f : dot / (na * nb);
 }
 
 // ---- aggregation ----------------------------------------------------------------------------------------------------
