@@ -95,6 +95,13 @@ uint64_t szb_resample_out_len(uint64_t n_in, uint32_t rate);
 szb_status szb_downmix_to_mono(szb_ctx* ctx, const int16_t* interleaved, uint64_t n_samples, uint32_t channels,
                                int16_t* mono, uint64_t mono_cap, uint64_t* n_mono);
 
+/* augment (lib.rs:103-116): circular shift < min(len, 800), gain U(0.95, 1.05), per-sample noise
+ * U(-l, l) * 32767 with l ~ U(0, 0.005), clamp, truncating cast.  The reference draws from an unseeded thread_rng; here
+ * every draw derives from `seed` (szb_augment_params returns the three clip-level draws). out must not alias in. */
+szb_status szb_augment_params(uint64_t seed, uint64_t n_samples, float* noise_level, float* gain, uint64_t* shift);
+szb_status szb_augment(szb_ctx* ctx, const int16_t* in, uint64_t n_samples, uint64_t seed, int16_t* out);
+szb_status szb_augment_dev(szb_ctx* ctx, const int16_t* d_in, uint64_t n_samples, uint64_t seed, int16_t* d_out);
+
 /* resample_to_44100 (lib.rs:186-209).  rate == 44100 copies.  Otherwise polyphase FIR (DESIGN.md "Resampler"),
  * output clamped to [-32768, 32767] and truncated toward zero like lib.rs:205-208. */
 szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in, uint32_t rate, int16_t* out,

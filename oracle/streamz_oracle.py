@@ -385,6 +385,23 @@ def train_batch(net: Net, x: np.ndarray, targets: np.ndarray, lr: float) -> None
         w -= (g * scale).astype(net.dtype)
 
 
+def augment(samples: np.ndarray, shift: int, gain: float, noise_level: float, key: int) -> np.ndarray:
+    """lib.rs:103-116 with the draws injected: out[i] = trunc(clamp(f32(s[(i+shift) % n]) * gain + noise_i * 32767)) where
+    noise_i = (2 u_i - 1) * noise_level and u_i = 24 bits of splitmix64(key ^ i) (this repo's counter stream).  All
+    products and the sum are rounded to float32 one at a time, like the Rust expression."""
+    s = np.asarray(samples, dtype=np.int16)
+    n = len(s)
+    if n == 0:
+        return s.copy()
+    i = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        u = (_splitmix64(np.uint64(key) ^ i) >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
+    f = np.float32
+    noise = ((f(2.0) * u).astype(f) - f(1.0)).astype(f) * f(noise_level)
+    val = (s[(np.arange(n) + int(shift)) % n].astype(f) * f(gain)).astype(f) + (noise.astype(f) * f(32767.0)).astype(f)
+    return np.trunc(np.clip(val.astype(f), f(-32768.0), f(32767.0))).astype(np.int16)
+
+
 # --- counter-based dropout stream (this repo's; the reference uses an unseeded thread_rng, lib.rs:123) ---------------
 
 _M64 = (1 << 64) - 1

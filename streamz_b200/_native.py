@@ -60,6 +60,9 @@ SIGNATURES = {
     "szb_num_windows": (u64, [u64]),
     "szb_resample_out_len": (u64, [u64, u32]),
     "szb_downmix_to_mono": (i32, [vp, vp, u64, u32, vp, u64, P(u64)]),
+    "szb_augment_params": (i32, [u64, u64, P(f32), P(f32), P(u64)]),
+    "szb_augment": (i32, [vp, vp, u64, u64, vp]),
+    "szb_augment_dev": (i32, [vp, vp, u64, u64, vp]),
     "szb_resample_to_44100": (i32, [vp, vp, u64, u32, vp, u64, P(u64)]),
     "szb_extract": (i32, [vp, vp, u64, vp, u64, P(u64)]),
     "szb_extract_batch": (i32, [vp, vp, vp, u32, u32, vp, u64, vp]),

@@ -146,6 +146,21 @@ def downmix_to_mono(samples, channels: int, ctx: Optional[Context] = None) -> np
     return out[: n.value]
 
 
+def augment_params(seed: int, n_samples: int) -> Tuple[float, float, int]:
+    nl, gain, shift = C.c_float(), C.c_float(), C.c_uint64()
+    N.check(N.lib.szb_augment_params(int(seed), int(n_samples), C.byref(nl), C.byref(gain), C.byref(shift)))
+    return float(nl.value), float(gain.value), int(shift.value)
+
+
+def augment(samples, seed: int = 0, ctx: Optional[Context] = None) -> np.ndarray:
+    """lib.rs:103-116 with every random draw derived from ``seed``."""
+    ctx = ctx or default_context()
+    s = _i16(samples)
+    out = np.empty_like(s)
+    N.check(N.lib.szb_augment(ctx.handle, N.ptr(s), len(s), int(seed), N.ptr(out)))
+    return out
+
+
 def resample_to_44100(samples, from_rate: int, ctx: Optional[Context] = None) -> np.ndarray:
     """lib.rs:186-209 (returns a new i16 array; rate 44100 is a copy)."""
     ctx = ctx or default_context()
@@ -421,6 +436,28 @@ def pretrain_from_features(net: SimpleNeuralNet, windows, target_class: int, num
     finally:
         data.close()
     return total / count if count else 0.0                        # lib.rs:623-627
+
+
+def pretrain_network(net: SimpleNeuralNet, samples, target_class: int, num_classes: int, epochs: int, lr: float, dropout: float,
+                     batch_size: int, extractor: FeatureExtractor, rng: Optional[np.random.Generator] = None, seed: int = 0) -> float:
+    """lib.rs:348-397: every epoch augments the clip, re-extracts its windows, shuffles and trains (augment -> extract
+    -> train all run on the GPU; the windows make one trip through the host API here)."""
+    assert num_classes == net.output_size()
+    rng = rng or np.random.default_rng(seed)
+    total, count = 0.0, 0
+    for e in range(int(epochs)):
+        windows = extractor.extract(augment(samples, seed=seed * 1000003 + e, ctx=net.ctx))     # lib.rs:368-369
+        if len(windows) == 0:
+            continue
+        data = DeviceFeatures(net.ctx, windows, np.full(len(windows), int(target_class), np.uint32))
+        try:
+            l, c = train_epoch(net, data, rng.permutation(len(windows)).astype(np.uint32), max(1, int(batch_size)), lr, dropout,
+                               seed=seed, stream=e)
+        finally:
+            data.close()
+        total += l
+        count += c
+    return total / count if count else 0.0
 
 
 def train_from_feature_map(net: SimpleNeuralNet, feature_map: Dict[str, np.ndarray], files: Iterable[Tuple[str, int]], epochs: int,

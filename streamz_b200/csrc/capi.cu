@@ -312,6 +312,50 @@ szb_status szb_downmix_to_mono(szb_ctx* ctx, const int16_t* in, uint64_t n, uint
     return SZB_OK;
 }
 
+static unsigned long long host_splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// augment (lib.rs:103-116).  Clip-level draws from the seed: noise_level U(0, 0.005), gain U(0.95, 1.05),
+// shift in [0, min(len, 800)) (lib.rs:105-107); the reference uses an unseeded thread_rng.
+szb_status szb_augment_params(uint64_t seed, uint64_t n_samples, float* noise_level, float* gain, uint64_t* shift) {
+    SZB_REQUIRE(noise_level && gain && shift, "szb_augment_params: NULL argument");
+    const unsigned long long k = host_splitmix64(seed ^ 0xA06DE27ull);
+    const float u0 = float(uint32_t(host_splitmix64(k ^ 1) >> 40)) * 5.9604644775390625e-08f;
+    const float u1 = float(uint32_t(host_splitmix64(k ^ 2) >> 40)) * 5.9604644775390625e-08f;
+    *noise_level = 0.005f * u0;
+    *gain = 0.95f + 0.1f * u1;
+    const uint64_t range = std::min<uint64_t>(n_samples, SZB_WINDOW_SIZE);
+    *shift = range ? host_splitmix64(k ^ 3) % range : 0;
+    return SZB_OK;
+}
+
+szb_status szb_augment_dev(szb_ctx* ctx, const int16_t* d_in, uint64_t n, uint64_t seed, int16_t* d_out) {
+    SZB_REQUIRE(ctx && (n == 0 || (d_in && d_out)), "szb_augment_dev: NULL argument");
+    SZB_REQUIRE(d_in != d_out || n == 0, "szb_augment_dev: in-place augmentation is not supported (circular shift)");
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    float nl, gain;
+    uint64_t shift;
+    SZB_TRY(szb_augment_params(seed, n, &nl, &gain, &shift));
+    return launch_augment(ctx, d_in, n, shift, gain, nl, host_splitmix64(seed ^ 0x5EEDull), d_out);
+}
+
+szb_status szb_augment(szb_ctx* ctx, const int16_t* in, uint64_t n, uint64_t seed, int16_t* out) {
+    SZB_REQUIRE(ctx && (n == 0 || (in && out)), "szb_augment: NULL argument");
+    if (n == 0) return SZB_OK;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->pcm.reserve(n * 2));
+    SZB_TRY(ctx->misc.reserve(n * 2));
+    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, in, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(szb_augment_dev(ctx, ctx->pcm.as<int16_t>(), n, seed, ctx->misc.as<int16_t>()));
+    SZB_CUDA(cudaMemcpyAsync(out, ctx->misc.ptr, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
 szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in, uint32_t rate, int16_t* out,
                                  uint64_t out_cap, uint64_t* n_out) {
     SZB_REQUIRE(ctx && n_out && (in || n_in == 0), "szb_resample_to_44100: NULL argument");

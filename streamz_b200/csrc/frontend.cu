@@ -407,6 +407,28 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
     }
 }
 
+// augment (lib.rs:103-116): circular shift, gain, uniform noise, clamp, truncating cast.  The three clip-level draws
+// (noise_level, gain, shift) are made on the host; the per-sample noise comes from the counter RNG below so the kernel
+// is reproducible and the oracle can restate it.  Arithmetic is done with explicitly rounded mul/add (no FMA
+// contraction), as the Rust expression `samples[idx] as f32 * gain + noise * i16::MAX as f32` rounds.
+__device__ __forceinline__ unsigned long long aug_splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void augment_kernel(const int16_t* __restrict__ in, uint64_t n, uint64_t shift, float gain, float noise_level,
+                               unsigned long long key, int16_t* __restrict__ out) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t idx = i + shift;
+        if (idx >= n) idx -= n;                                           // (i + shift) % len, shift < len
+        const float u = float(uint32_t(aug_splitmix64(key ^ i) >> 40)) * 5.9604644775390625e-08f;   // [0, 1)
+        const float noise = __fmul_rn(__fsub_rn(__fmul_rn(2.f, u), 1.f), noise_level);               // U(-nl, nl)
+        const float val = __fadd_rn(__fmul_rn(float(in[idx]), gain), __fmul_rn(noise, 32767.f));     // lib.rs:112
+        out[i] = int16_t(__float2int_rz(fminf(fmaxf(val, -32768.f), 32767.f)));                      // lib.rs:113
+    }
+}
+
 // downmix_to_mono (lib.rs:172-183)
 __global__ void downmix_kernel(const int16_t* __restrict__ in, uint64_t n_in, uint32_t ch, int16_t* __restrict__ out,
                                uint64_t n_out) {
@@ -590,6 +612,17 @@ szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_
     if (D == 1) SZB_TRY(launch_resample_t<1>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
     else if (D == 3) SZB_TRY(launch_resample_t<3>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
     else SZB_TRY(launch_resample_t<5>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
+    ctx->launches += 1;
+    return SZB_OK;
+}
+
+szb_status launch_augment(szb_ctx* ctx, const int16_t* d_in, uint64_t n, uint64_t shift, float gain, float noise_level, uint64_t key,
+                          int16_t* d_out) {
+    if (n == 0) return SZB_OK;
+    const int threads = 256;
+    const uint64_t blocks = std::min<uint64_t>((n + threads - 1) / threads, uint64_t(ctx->sm_count) * 16);
+    augment_kernel<<<uint32_t(blocks), threads, 0, ctx->stream>>>(d_in, n, shift, gain, noise_level, key, d_out);
+    SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return SZB_OK;
 }

@@ -148,3 +148,30 @@ def test_capacity_and_argument_errors(sz, ctx, native, oracle):
     assert st == native.ERR_INVALID and b"capacity" in native.lib.szb_last_error()
     assert n.value == oracle.n_windows(len(clip))                                   # size is still reported
     assert native.lib.szb_resample_to_44100(ctx.handle, None, 0, 0, None, 0, C.byref(n)) == native.ERR_INVALID
+
+
+def test_augment_is_integer_exact(sz, ctx, oracle, native):
+    # lib.rs:103-116 with the random draws derived from the seed
+    clip = oracle.synth_clip(1, 5, 0.6)
+    for seed in (0, 1, 12345):
+        nl, gain, shift = sz.augment_params(seed, len(clip))
+        assert 0 <= nl < 0.005 and 0.95 <= gain < 1.05 and 0 <= shift < 800        # lib.rs:105-107
+        key = int(oracle._splitmix64(np.array([seed ^ 0x5EED], dtype=np.uint64))[0])
+        got = sz.augment(clip, seed, ctx)
+        assert got.dtype == np.int16 and np.array_equal(got, oracle.augment(clip, shift, gain, nl, key))
+    short = clip[:100]
+    assert sz.augment_params(7, len(short))[2] < 100                                # shift < len for short clips
+    assert len(sz.augment(np.zeros(0, np.int16), 3, ctx)) == 0
+    loud = np.full(5000, 32767, np.int16)                                           # gain > 1 must clamp, not wrap
+    assert sz.augment(loud, 4, ctx).max() <= 32767 and sz.augment(-loud - 1, 4, ctx).min() >= -32768
+
+
+def test_pretrain_network_runs_augment_extract_train(sz, ctx, oracle):
+    # lib.rs:348-397: per epoch augment -> extract -> shuffle -> train
+    ex = sz.FeatureExtractor(ctx)
+    net = sz.SimpleNeuralNet(60, 512, 256, 2, seed=3, ctx=ctx)
+    clip = oracle.synth_clip(0, 9, 1.0)
+    first = sz.pretrain_network(net, clip, 0, 2, 1, 0.01, 0.2, 8, ex, seed=1)
+    later = sz.pretrain_network(net, clip, 0, 2, 3, 0.01, 0.2, 8, ex, seed=2)
+    assert np.isfinite(first) and later < first
+    assert sz.pretrain_network(net, clip[:500], 0, 2, 2, 0.01, 0.2, 8, ex) == 0.0   # no windows -> 0 (lib.rs:392-396)
