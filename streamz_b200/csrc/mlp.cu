@@ -135,20 +135,12 @@ __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, 
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     float* zr = z + size_t(row) * ldz;
-    float mx = -INFINITY;
-    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, zr[c]);                     // lib.rs:887
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += expf(zr[c] - mx);                   // lib.rs:888-889
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const bool ok = valid ? valid[row] != 0 : true;
     const uint32_t label = labels ? labels[row] : 0xffffffffu;
     float best = -1.f;
     int best_c = -1;
-    for (int c = lane; c < C; c += 32) {
-        const float p = expf(zr[c] - mx) / sum;                                   // lib.rs:890
+    // per-element consumer shared by both paths
+    auto consume = [&](int c, float p) {
         if (mode & 1) probs[size_t(row) * C + c] = p;
         if (mode & 2) {
             const float t = target_vec ? target_vec[c] : (uint32_t(c) == label ? 1.f : 0.f);
@@ -159,6 +151,42 @@ __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, 
         }
         if (mode & 4) { if (p >= best) { best = p; best_c = c; } }                // last maximal element wins
         if ((mode & 8) && ok) atomicAdd(&sums[c], p);
+    };
+    if (C <= 128) {
+        // the whole row lives in registers: one read of the logits, one expf per element
+        float v[4], e[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            v[q] = c < C ? zr[c] : -INFINITY;
+            mx = fmaxf(mx, v[q]);                                                 // lib.rs:887
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            e[q] = lane + 32 * q < C ? expf(v[q] - mx) : 0.f;                     // lib.rs:888
+            sum += e[q];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            if (c < C) consume(c, e[q] / sum);                                    // lib.rs:890
+        }
+    } else {
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, zr[c]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) sum += expf(zr[c] - mx);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int c = lane; c < C; c += 32) consume(c, expf(zr[c] - mx) / sum);
     }
     if (mode & 4) {
 #pragma unroll
@@ -170,6 +198,75 @@ __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, 
         if (lane == 0 && best_c >= 0 && best >= threshold) atomicAdd(&hist[best_c], 1ull);  // lib.rs:1398-1400
     }
     if ((mode & 2) && lane == 0 && ok) atomicAdd(&tail[0], 1.f);
+}
+
+
+// Training softmax for C <= 128 (one CTA = 32 rows, one warp per row): softmax, delta3 = p - t (lib.rs:1028) written
+// in place AND as a [C][32]-row tile staged in shared memory so the transposed copy leaves with 128-byte coalesced
+// stores; loss (lib.rs:611-615) and surviving-window count are reduced inside the CTA: two atomics per 32 rows.
+__global__ void __launch_bounds__(1024) softmax_train_kernel(float* __restrict__ z, int rows, int C, const uint32_t* __restrict__ labels,
+                                                            const float* __restrict__ target_vec, const uint8_t* __restrict__ valid,
+                                                            float* __restrict__ tail, float* __restrict__ zT, int ldzT) {
+    __shared__ float tile[128][33];
+    __shared__ float s_loss[32], s_cnt[32];
+    const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+    const int row0 = blockIdx.x * 32, row = row0 + wrow;
+    float loss = 0.f, cnt = 0.f;
+    if (row < rows) {
+        float* zr = z + size_t(row) * C;
+        const bool ok = valid ? valid[row] != 0 : true;
+        const uint32_t label = labels ? labels[row] : 0xffffffffu;
+        float v[4], e[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            v[q] = c < C ? zr[c] : -INFINITY;
+            mx = fmaxf(mx, v[q]);                                                 // lib.rs:1023
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            e[q] = lane + 32 * q < C ? expf(v[q] - mx) : 0.f;                     // lib.rs:1024
+            sum += e[q];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            if (c < C) {
+                const float p = e[q] / sum;                                       // lib.rs:1026
+                const float t = target_vec ? target_vec[c] : (uint32_t(c) == label ? 1.f : 0.f);
+                const float d3 = ok ? p - t : 0.f;
+                zr[c] = d3;
+                tile[c][wrow] = d3;
+                if (ok && !target_vec && uint32_t(c) == label) loss = -logf(fmaxf(p, 1e-12f));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+        cnt = ok ? 1.f : 0.f;
+    }
+    if (lane == 0) { s_loss[wrow] = loss; s_cnt[wrow] = cnt; }
+    __syncthreads();
+    const int nrows = min(32, rows - row0);
+    for (int c = wrow; c < C; c += 32)
+        if (lane < nrows) zT[size_t(c) * ldzT + row0 + lane] = tile[c][lane];
+    if (wrow == 0) {
+        float l = s_loss[lane], n = s_cnt[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            l += __shfl_xor_sync(0xffffffffu, l, o);
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+        }
+        if (lane == 0) {
+            if (n > 0.f) atomicAdd(&tail[0], n);
+            if (l != 0.f) atomicAdd(&tail[1], l);
+        }
+    }
 }
 
 // Column sums of D[rows][cols] accumulated into g[cols] (bias gradients, lib.rs:1033,1038,1044).
@@ -357,7 +454,13 @@ static szb_status refresh_wt(szb_net* net) {
 
 template <int EPI>
 static szb_status gemm_tc(szb_net* net, tc::GemmArgs g, int split_k = 1) {
-    return net->precision == 2 ? tc::launch_gemm_tc<128, 1, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 3, EPI>(net->ctx, g, split_k);
+    // 128 x 128 tiles unless that grid would leave most of the 148 SMs idle (the per-step GEMMs are small): then
+    // 128 x 64 tiles double the CTA count
+    const int tiles128 = ((g.M + 127) / 128) * ((g.N + 127) / 128) * std::max(1, split_k);
+    const bool narrow = tiles128 * 10 < net->ctx->sm_count * 7 && g.N > 64;
+    if (net->precision == 2)
+        return narrow ? tc::launch_gemm_tc<64, 1, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 1, EPI>(net->ctx, g, split_k);
+    return narrow ? tc::launch_gemm_tc<64, 3, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 3, EPI>(net->ctx, g, split_k);
 }
 
 // forward for rows already in d_x (device); leaves logits in a_z; activations in a_h1 / a_h2
@@ -423,6 +526,13 @@ static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, co
     if (B <= 0) return SZB_OK;
     const int wpb = 8;
     float* tail = net->grads.as<float>() + net->n_params();
+    if (mode == 2 && zT && net->n_out <= 128) {   // tensor-core training path
+        softmax_train_kernel<<<(B + 31) / 32, 1024, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out), labels, target_vec, valid,
+                                                                          tail, zT, B);
+        SZB_CUDA(cudaGetLastError());
+        net->ctx->launches += 1;
+        return SZB_OK;
+    }
     softmax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out),
                                                                           int(net->n_out), mode, probs, labels, target_vec,
                                                                           valid, tail, threshold, hist, sums, zT, B);
