@@ -49,6 +49,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, windows_per_launch):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture, or (None, why)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))[kernel]
+        per_win = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["windows_per_launch"]
+        how = f"ncu dram__bytes_read.sum + dram__bytes_write.sum, {d['source']}"
+        if d["windows_per_launch"] != windows_per_launch:
+            how += f"; scaled from a {d['windows_per_launch']}-window launch"
+        return int(per_win * windows_per_launch), how
+    except Exception as e:
+        return None, f"no capture ({e!r})"
+
+
 # ---- synthetic multi-speaker clips, generated on the device (plumbing, outside every timed region) --------------------
 def synth_clips_device(torch, device, n_clips, n_samples, rate, seed):
     """[n_clips, n_samples] int16: harmonic stack with speaker-specific pitch and formants, syllable envelope, -30 dBFS
@@ -94,7 +108,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -150,13 +164,20 @@ def cpu_reference_rate(n_clips_sample, threads, steps=1, warmup=0, seed=1):
     return n_clips_sample * CLIP_SECONDS / dt, dt
 
 
+def cpu_sample_for(seconds, threads, cap):
+    """Number of clips whose CPU extraction takes about `seconds` on this host (probe with a few clips per thread first)."""
+    probe = int(min(cap, max(16, threads * 4)))
+    rate, _ = cpu_reference_rate(probe, threads)
+    return int(min(cap, max(probe, rate * seconds / CLIP_SECONDS)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    # bounded sample: ~2 clips per core per step keeps K + W steps within a couple of minutes on any host
-    sample = int(min(N_CLIPS, max(16, cores * 4)))
+    # bounded sample: about 3 s of host work per step keeps K + W steps within a couple of minutes on any host
+    sample = cpu_sample_for(3.0, cores, N_CLIPS)
     rate, dt = cpu_reference_rate(sample, cores, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "audio-seconds/sec MFCC+delta extraction", "value": rate, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -173,7 +194,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=N_CLIPS, help="clips per GPU (default: the full configs[1] batch)")
@@ -326,6 +347,7 @@ def main():
     algo_bytes = windows_per_launch * BYTES_PER_WINDOW_44K
     k_avg_ms = k_ms / max(1, k_n)
     achieved = algo_bytes / (k_avg_ms * 1e-3) / 1e9 if k_n else None
+    traffic, traffic_src = measured_traffic("extract_kernel", windows_per_launch)
     line = {
         "metric": "audio-seconds/sec MFCC+delta extraction", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -337,15 +359,15 @@ def main():
                 "steps": e2e_steps, "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "kernel": "extract_kernel", "launch_ms": k_avg_ms, "launches_timed": int(k_n),
+                     "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "kernel": "extract_kernel", "launch_ms": k_avg_ms, "launches_timed": int(k_n),
                      "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                      "note": "1040 B/window (800 read + 240 written) x windows per launch / CUDA-event launch time"},
         "clocks": clocks, "mlp": mlp,
     }
     if not args.no_cpu and world >= 1:
         cores = os.cpu_count() or 1
-        sample = int(min(n_clips, max(16, cores * 8)))
         try:
+            sample = cpu_sample_for(12.0, cores, n_clips)      # about 10-30 s of CPU work, bounded by the workload itself
             rate, dt = cpu_reference_rate(sample, cores, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} of {n_clips} clips, C restatement of lib.rs:186-345 (oracle/oracle.c), one clip per thread, {dt:.2f} s"}

@@ -580,8 +580,8 @@ static szb_status launch_resample_t(szb_ctx* ctx, dim3 grid, uint32_t threads, s
     return SZB_OK;
 }
 
-szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
-                           uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
+szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
+                                   uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
     if (n_clips == 0 || max_out == 0) return SZB_OK;
     uint32_t L, M;
     resample_ratio(rate, L, M);

@@ -26,6 +26,9 @@ szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin
                           bool aligned16);
 szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
                            uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out);
+// any rational ratio with L <= 4096 (frontend.cu); launch_resample (resample.cu) uses it for the ratios its row kernel cannot take
+szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
+                                   uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out);
 szb_status launch_augment(szb_ctx* ctx, const int16_t* d_in, uint64_t n, uint64_t shift, float gain, float noise_level, uint64_t key,
                           int16_t* d_out);
 szb_status launch_downmix(szb_ctx* ctx, const int16_t* d_in, uint64_t n_in, uint32_t ch, int16_t* d_out, uint64_t n_out);

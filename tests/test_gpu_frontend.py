@@ -105,7 +105,8 @@ def test_downmix(sz, ctx, oracle):
         assert np.array_equal(sz.downmix_to_mono(s, ch, ctx), oracle.downmix_to_mono(s, ch))
 
 
-@pytest.mark.parametrize("rate", [8000, 11025, 16000, 22050, 32000, 48000])
+# 37800 (L/M = 7/6) and 44000 (441/440) take the generic kernel, the others the lane = row kernel (resample.cu)
+@pytest.mark.parametrize("rate", [8000, 11025, 12000, 16000, 22050, 24000, 32000, 37800, 44000, 48000])
 def test_resampler_is_bit_exact(sz, ctx, oracle, native, rate):
     x = oracle.synth_clip(2, rate, 0.7, rate=rate)
     L, M = oracle.resample_ratio(rate)
