@@ -12,7 +12,9 @@
 // between tiles), each feature row is written once with 16-byte coalesced stores; MFCCs of the previous tile stay in
 // a shared-memory ring so the +-2-frame delta stencil never recomputes or re-reads anything inside a segment.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <numeric>
 
 #include "common.cuh"
 #include "fft_math.cuh"
@@ -313,8 +315,8 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
 // result bits are unchanged): 5.7 shared loads and 17 FMAs per output instead of 16 + 16.
 constexpr int kResRows = 32;
 
-template <int D>
-__global__ void __launch_bounds__(160, 4)
+template <int K, int D>   // K adjacent outputs per thread, whose windows start at most D input samples apart
+__global__ void __launch_bounds__(160, (K <= 3 ? 4 : (K <= 4 ? 3 : 2)))
 resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ out_off,
                 uint32_t n_clips, const float* __restrict__ taps, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G, uint32_t rate,
                 int16_t* __restrict__ out) {
@@ -327,12 +329,12 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
     const uint32_t tid = threadIdx.x, g = tid;
     const bool worker = g < G;
     uint32_t q0 = 0;
-    float c[3][W];
+    float c[K][W];
     if (worker) {
-        q0 = uint32_t((uint64_t(3 * g) * M) / L);
+        q0 = uint32_t((uint64_t(K * g) * M) / L);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint64_t pos = uint64_t(3 * g + k) * M;
+        for (int k = 0; k < K; ++k) {
+            const uint64_t pos = uint64_t(K * g + k) * M;
             const uint32_t p = uint32_t(pos % L), d = uint32_t(pos / L) - q0;
             const float* cp = taps + size_t(p) * kResTaps;
 #pragma unroll
@@ -377,15 +379,17 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
                     float w[W];
 #pragma unroll
                     for (int t = 0; t < W; ++t) w[t] = wv[t];
-                    float acc[3] = { 0.f, 0.f, 0.f };
+                    float acc[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] = 0.f;
 #pragma unroll
                     for (int t = 0; t < W; ++t) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) acc[k] = fmaf(c[k][t], w[t], acc[k]);
+                        for (int k = 0; k < K; ++k) acc[k] = fmaf(c[k][t], w[t], acc[k]);
                     }
-                    int16_t* so = s_out + shift + r * Lb + 3 * g;
+                    int16_t* so = s_out + shift + r * Lb + K * g;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) so[k] = int16_t(__float2int_rz(fminf(fmaxf(acc[k], -32768.f), 32767.f)));
+                    for (int k = 0; k < K; ++k) so[k] = int16_t(__float2int_rz(fminf(fmaxf(acc[k], -32768.f), 32767.f)));
                 }
             }
             __syncthreads();
@@ -569,24 +573,24 @@ szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin
     return SZB_OK;
 }
 
-template <int D>
+template <int K, int D>
 static szb_status launch_resample_t(szb_ctx* ctx, dim3 grid, uint32_t threads, size_t smem, const int16_t* d_in, const uint64_t* d_in_off,
                                     const uint64_t* d_out_off, uint32_t n_clips, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G,
                                     uint32_t rate, int16_t* d_out) {
-    SZB_CUDA(cudaFuncSetAttribute(resample_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    resample_kernel<D><<<grid, threads, smem, ctx->stream>>>(d_in, d_in_off, d_out_off, n_clips, ctx->taps.as<float>(), L, M, Lb, G,
-                                                              rate, d_out);
+    SZB_CUDA(cudaFuncSetAttribute(resample_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    resample_kernel<K, D><<<grid, threads, smem, ctx->stream>>>(d_in, d_in_off, d_out_off, n_clips, ctx->taps.as<float>(), L, M, Lb, G,
+                                                                 rate, d_out);
     SZB_CUDA(cudaGetLastError());
     return SZB_OK;
 }
 
-szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
-                                   uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
-    if (n_clips == 0 || max_out == 0) return SZB_OK;
+template <int K>
+static szb_status launch_resample_k(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
+                                    uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
     uint32_t L, M;
     resample_ratio(rate, L, M);
-    // three adjacent outputs span at most ceil(2 M / L) input samples
-    const uint32_t span = uint32_t((2ull * M + L - 1) / L);
+    // K adjacent outputs span at most ceil((K - 1) M / L) input samples
+    const uint32_t span = uint32_t((uint64_t(K - 1) * M + L - 1) / L);
     SZB_REQUIRE(span <= 5 && L <= 4096, "resample: unsupported rate %u (L = %u, M = %u)", rate, L, M);
     if (ctx->taps_rate != rate) {
         const auto taps = resample_taps(rate);
@@ -595,12 +599,12 @@ szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint
         SZB_CUDA(cudaStreamSynchronize(ctx->stream));  // taps is a temporary
         ctx->taps_rate = rate;
     }
-    const uint32_t Lp = L % 3 == 0 ? L : 3 * L;             // lcm(L, 3)
-    const uint32_t mult = std::max<uint32_t>(1, 3 * 128 / Lp);
-    const uint32_t Lb = Lp * mult, G = Lb / 3;              // G threads cover one row of Lb outputs
+    const uint32_t Lp = L / std::gcd(L, uint32_t(K)) * K;   // lcm(L, K)
+    const uint32_t mult = std::max<uint32_t>(1, K * 128 / Lp);
+    const uint32_t Lb = Lp * mult, G = Lb / K;              // G threads cover one row of Lb outputs
     SZB_REQUIRE(G <= 160, "resample: rate %u needs %u threads per row", rate, G);
     const uint32_t threads = (G + 31) / 32 * 32;
-    const uint32_t D = span <= 1 ? 1 : (span <= 3 ? 3 : 5);
+    const uint32_t D = std::max<uint32_t>(1, span);
     const uint64_t in_per_row = uint64_t(Lb) * M / L;
     const size_t smem = ((size_t(kResRows) * in_per_row + kResTaps + D) * 4 + 15) / 16 * 16 + (size_t(kResRows) * Lb + 16) * 2;
     SZB_REQUIRE(smem <= 200 * 1024, "resample: rate %u needs %zu bytes of shared memory", rate, smem);
@@ -609,11 +613,23 @@ szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint
     const uint64_t want_x = std::max<uint64_t>(1, (uint64_t(ctx->sm_count) * 16 + gy - 1) / gy);
     const uint32_t gx = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(want_x, tiles)));
     dim3 grid(gx, gy);
-    if (D == 1) SZB_TRY(launch_resample_t<1>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
-    else if (D == 3) SZB_TRY(launch_resample_t<3>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
-    else SZB_TRY(launch_resample_t<5>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out));
+    if (D == 1) SZB_TRY((launch_resample_t<K, 1>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out)));
+    else if (D == 2) SZB_TRY((launch_resample_t<K, 2>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out)));
+    else if (D == 4) SZB_TRY((launch_resample_t<K, 4>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out)));
+    else if (D == 3) SZB_TRY((launch_resample_t<K, 3>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out)));
+    else SZB_TRY((launch_resample_t<K, 5>(ctx, grid, threads, smem, d_in, d_in_off, d_out_off, n_clips, L, M, Lb, G, rate, d_out)));
     ctx->launches += 1;
     return SZB_OK;
+}
+
+szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
+                                   uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
+    if (n_clips == 0 || max_out == 0) return SZB_OK;
+    static const int k_env = [] { const char* e = getenv("SZB_RES_K"); return e ? atoi(e) : 3; }();
+    if (k_env == 4) return launch_resample_k<4>(ctx, d_in, d_in_off, d_out_off, n_clips, max_out, rate, d_out);
+    if (k_env == 5) return launch_resample_k<5>(ctx, d_in, d_in_off, d_out_off, n_clips, max_out, rate, d_out);
+    if (k_env == 6) return launch_resample_k<6>(ctx, d_in, d_in_off, d_out_off, n_clips, max_out, rate, d_out);
+    return launch_resample_k<3>(ctx, d_in, d_in_off, d_out_off, n_clips, max_out, rate, d_out);
 }
 
 szb_status launch_augment(szb_ctx* ctx, const int16_t* d_in, uint64_t n, uint64_t shift, float gain, float noise_level, uint64_t key,

@@ -290,14 +290,18 @@ __global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
 // Raw FP32 K-slabs flow global -> shared with cp.async (LDGSTS, zero-filled past the matrix edge) through a ring of
 // kAStages stages, issued two k-blocks ahead of the tensor core; each thread then turns ITS OWN sixteen 16-byte chunks
 // into the hi tile (in place) and the lo tile (3xTF32), so no barrier is needed between the copy and the split.
-constexpr int kAStages = 4;
-
+// The copies run kDist k-blocks ahead of the tensor core through a ring of kDist + 2 stages (the slot refilled at
+// iteration kb held k-block kb - 2, whose MMAs are the ones the producers wait for anyway before reusing a lo buffer).
+// MEASURED ON B200: deepening the distance from 2 to 5 k-blocks does not move the training step (180 vs 183 us at batch
+// 4096): the step is bound by the chain of 14 dependent launches, not by operand latency inside a GEMM.  Kept at 2.
 template <int BN, int PASSES>
 struct SmemLayoutAsync {
     static constexpr int kATile = BM * BK * 4;
     static constexpr int kBTile = BN * BK * 4;
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kLoBytes = PASSES == 3 ? 2 * kStageBytes : 0;
+    static constexpr int kDist = 2;
+    static constexpr int kAStages = kDist + 2;
     static constexpr int kTotal = kAStages * kStageBytes + kLoBytes;
 };
 
@@ -319,6 +323,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const GemmArgs g) {
     using SL = SmemLayoutAsync<BN, PASSES>;
+    constexpr int kAStages = SL::kAStages, kDist = SL::kDist;
     extern __shared__ __align__(1024) unsigned char tc_smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
     __shared__ uint64_t s_full[kAStages], s_free[kAStages];
     __shared__ uint32_t s_tmem;
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t smem_base = smem_u32(tc_smem);
     if ((smem_base & 1023u) != 0) __trap();
-    const uint32_t lo_base = smem_base + kAStages * SL::kStageBytes;
+    const uint32_t lo_base = smem_base + SL::kAStages * SL::kStageBytes;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
     const int n_kb = (kb1 - kb0 + BK - 1) / BK;
@@ -373,16 +378,16 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
                            ok ? static_cast<const void*>(g.B + size_t(gr) * g.ldb + gk) : static_cast<const void*>(g.B), ok ? kbytes : 0u);
             }
         };
-        for (int j = 0; j < 2; ++j) {            // prologue: two k-blocks in flight
+        for (int j = 0; j < kDist; ++j) {        // prologue: kDist k-blocks in flight
             if (j < n_kb) issue(j);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         for (int kb = 0; kb < n_kb; ++kb) {
-            // MMAs of k-block kb - 2 done => raw stage (kb + 2) % kAStages and lo buffer kb % 2 are free again
+            // MMAs of k-block kb - 2 done => raw stage (kb + kDist) % kAStages and lo buffer kb % 2 are free again
             if (kb >= 2) mbar_wait(&s_free[(kb - 2) % kAStages], uint32_t(((kb - 2) / kAStages) & 1));
-            if (kb + 2 < n_kb) issue(kb + 2);
+            if (kb + kDist < n_kb) issue(kb + kDist);
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's chunks of k-block kb have landed
+            asm volatile("cp.async.wait_group %0;" ::"n"(kDist) : "memory");   // this thread's chunks of k-block kb have landed
             const uint32_t st = smem_base + (kb % kAStages) * SL::kStageBytes;
             const uint32_t lo = lo_base + (kb & 1) * SL::kStageBytes;
             if (PASSES == 3) {
