@@ -70,10 +70,6 @@ szb_status szb_timer_stop(szb_ctx* ctx, float* elapsed_ms);
  * CUDA events around each launch when enabled (used for the roofline figure; off by default). */
 szb_status szb_kernel_timing(szb_ctx* ctx, int32_t enable);
 szb_status szb_kernel_timing_read(szb_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset);
-/* The resampler has two kernels with identical results: a generic one and a lane = row one for the common rates that
- * needs at least `min_tiles` warp tiles (32 rows of 40-80 ms) per launch to fill the machine.  Default: one tile per
- * resident warp.  0 forces the row kernel whenever the rate and clip length allow it (tests do that). */
-szb_status szb_set_resample_rows_min_tiles(szb_ctx* ctx, uint64_t min_tiles);
 
 /* device memory helpers for FFI hosts that have no CUDA binding of their own */
 szb_status szb_dev_alloc(szb_ctx* ctx, size_t bytes, void** dptr);

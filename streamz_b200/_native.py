@@ -48,7 +48,6 @@ SIGNATURES = {
     "szb_timer_stop": (i32, [vp, P(f32)]),
     "szb_kernel_timing": (i32, [vp, i32]),
     "szb_kernel_timing_read": (i32, [vp, P(f64), P(u64), i32]),
-    "szb_set_resample_rows_min_tiles": (i32, [vp, u64]),
     "szb_dev_alloc": (i32, [vp, sz, P(vp)]),
     "szb_dev_free": (i32, [vp, vp]),
     "szb_memcpy_h2d": (i32, [vp, vp, vp, sz]),

@@ -78,10 +78,6 @@ class Context:
     def kernel_timing(self, enable: bool):
         N.check(N.lib.szb_kernel_timing(self.handle, 1 if enable else 0))
 
-    def set_resample_rows_min_tiles(self, min_tiles: int):
-        """0 forces the lane = row resampling kernel whenever the rate allows it; see include/streamz_b200.h."""
-        N.check(N.lib.szb_set_resample_rows_min_tiles(self.handle, int(min_tiles)))
-
     def kernel_timing_read(self, reset: bool = True) -> Tuple[float, int]:
         ms, n = C.c_double(), C.c_uint64()
         N.check(N.lib.szb_kernel_timing_read(self.handle, C.byref(ms), C.byref(n), 1 if reset else 0))

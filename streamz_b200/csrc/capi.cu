@@ -154,7 +154,7 @@ void szb_ctx_destroy(szb_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
-    for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->rows_taps, &ctx->labels, &ctx->misc, &ctx->probs,
+    for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
                        &ctx->x })
         b->release();
     ctx->h_segs.release();
@@ -190,11 +190,6 @@ szb_status szb_timer_stop(szb_ctx* ctx, float* elapsed_ms) {
 szb_status szb_kernel_timing(szb_ctx* ctx, int32_t enable) {
     SZB_REQUIRE(ctx, "szb_kernel_timing: ctx is NULL");
     ctx->ktime_on = enable != 0;
-    return SZB_OK;
-}
-szb_status szb_set_resample_rows_min_tiles(szb_ctx* ctx, uint64_t min_tiles) {
-    SZB_REQUIRE(ctx, "szb_set_resample_rows_min_tiles: ctx is NULL");
-    ctx->rows_min_tiles = min_tiles;
     return SZB_OK;
 }
 szb_status szb_kernel_timing_read(szb_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset) {
@@ -382,7 +377,7 @@ szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in,
     SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream));
     SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, in, n_in * 2, cudaMemcpyHostToDevice, ctx->stream));
     SZB_TRY(launch_resample(ctx, ctx->pcm.as<int16_t>(), ctx->labels.as<uint64_t>(), ctx->labels.as<uint64_t>() + 2, 1, n,
-                            rate, ctx->misc.as<int16_t>(), true));
+                            rate, ctx->misc.as<int16_t>()));
     SZB_CUDA(cudaMemcpyAsync(out, ctx->misc.ptr, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SZB_OK;
@@ -483,8 +478,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
         if (resample) {
             uint64_t max_out = 0;
             for (uint32_t c = c0; c < c1; ++c) max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
-            // batch_layout pads every resampled clip to 8 samples and misc comes from cudaMalloc: 16-byte aligned outputs
-            SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>(), true));
+            SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
         }
         SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats, aligned16));
         if (piped) {

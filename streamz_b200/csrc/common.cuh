@@ -74,9 +74,6 @@ struct szb_ctx {
     szb::DevBuf segs, counter, pcm, feats, taps, labels, misc, probs, x;
     szb::PinnedBuf h_segs, h_misc;
     uint32_t taps_rate = 0;  // rate the taps buffer currently holds
-    szb::DevBuf rows_taps;   // taps in output order for the lane = row resampler (resample.cu)
-    uint32_t rows_taps_rate = 0;
-    uint64_t rows_min_tiles = ~0ull;   // ~0: default (one warp tile per resident warp); see szb_set_resample_rows_min_tiles
     // NCCL (loaded lazily with dlopen; see comm.cu)
     void* nccl_comm = nullptr;
     cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the rest of the backward pass

@@ -24,12 +24,8 @@ void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_
 szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint32_t n_queues);
 szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats,
                           bool aligned16);
-// out_aligned16: d_out is 16-byte aligned and every out_off is a multiple of 8 samples (lets the row kernel store vectors)
 szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
-                           uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out, bool out_aligned16);
-// any rational ratio with L <= 4096 (frontend.cu); launch_resample (resample.cu) uses it for the ratios its row kernel cannot take
-szb_status launch_resample_generic(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
-                                   uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out);
+                           uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out);
 szb_status launch_augment(szb_ctx* ctx, const int16_t* d_in, uint64_t n, uint64_t shift, float gain, float noise_level, uint64_t key,
                           int16_t* d_out);
 szb_status launch_downmix(szb_ctx* ctx, const int16_t* d_in, uint64_t n_in, uint32_t ch, int16_t* d_out, uint64_t n_out);

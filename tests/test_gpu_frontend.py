@@ -105,7 +105,6 @@ def test_downmix(sz, ctx, oracle):
         assert np.array_equal(sz.downmix_to_mono(s, ch, ctx), oracle.downmix_to_mono(s, ch))
 
 
-# 37800 (L/M = 7/6) and 44000 (441/440) take the generic kernel, the others the lane = row kernel (resample.cu)
 @pytest.mark.parametrize("rate", [8000, 11025, 12000, 16000, 22050, 24000, 32000, 37800, 44000, 48000])
 def test_resampler_is_bit_exact(sz, ctx, oracle, native, rate):
     x = oracle.synth_clip(2, rate, 0.7, rate=rate)
@@ -120,31 +119,6 @@ def test_resampler_is_bit_exact(sz, ctx, oracle, native, rate):
     assert (got != indep).mean() < 1e-3
     loud = np.where(np.arange(3000) % 40 < 20, 32767, -32768).astype(np.int16)     # overshoot must clamp (lib.rs:207)
     assert np.array_equal(sz.resample_to_44100(loud, rate, ctx), oracle.resample_to_44100(loud, rate, taps))
-
-
-@pytest.mark.parametrize("rate", [8000, 11025, 12000, 16000, 22050, 24000, 32000, 48000])
-def test_row_resampler_is_bit_exact(sz, oracle, native, rate):
-    """The lane = row kernel (resample.cu), forced on: single clips of awkward lengths (partial last row, partial last
-    block, first row starting at the clip edge) and a ragged batch through extract_batch, against the oracle."""
-    c2 = sz.Context(0)
-    c2.set_resample_rows_min_tiles(0)
-    L, M = oracle.resample_ratio(rate)
-    taps = np.zeros((L, 16), np.float32)
-    native.check(native.lib.szb_table_resample_taps(rate, taps.ctypes.data_as(C.c_void_p), None, None))
-    r = np.random.default_rng(rate)
-    for seconds in (0.93, 1.7, 3.001):
-        n = int(rate * seconds) + int(r.integers(0, 50))
-        x = (r.standard_normal(n) * 6000).clip(-32768, 32767).astype(np.int16)
-        x[: n // 3] = oracle.synth_clip(1, rate + n, n / rate, rate=rate)[: n // 3]
-        got = sz.resample_to_44100(x, rate, c2)
-        want = oracle.resample_to_44100(x, rate, taps)
-        assert got.shape == want.shape and np.array_equal(got, want), (rate, n, int(np.argmax(got != want)))
-    loud = np.where(np.arange(int(rate * 1.2)) % 40 < 20, 32767, -32768).astype(np.int16)   # overshoot must clamp (lib.rs:207)
-    assert np.array_equal(sz.resample_to_44100(loud, rate, c2), oracle.resample_to_44100(loud, rate, taps))
-    ex2 = sz.FeatureExtractor(c2)
-    clips = [oracle.synth_clip(s, 7 * s + rate, 1.0 + 0.37 * s, rate=rate) for s in range(4)]
-    for got, c in zip(ex2.extract_batch(clips, rate), clips):
-        assert np.array_equal(got, ex2.extract(oracle.resample_to_44100(c, rate, taps)))
 
 
 def test_resample_identity_and_empty(sz, ctx):
