@@ -636,9 +636,11 @@ static szb_status launch_resample_k(szb_ctx* ctx, const int16_t* d_in, const uin
     return SZB_OK;
 }
 
-// MEASURED ALTERNATIVES (git history, DESIGN.md "Resampler"): K = 6 outputs per thread (12.1 ms on C2 against 8.8 ms: the
-// 168 registers halve the occupancy), and a lane = row kernel with warp-uniform taps (constant bank: 45 ms, the 28 KB
-// table thrashes the constant cache; shared memory: 9.2 ms, 16 operand words per output through the LSU).
+// MEASURED ALTERNATIVES (git history, DESIGN.md "Resampler"), none faster than this kernel's 8.8 ms on C2: K = 6 outputs
+// per thread (12.1 ms: 168 registers halve the occupancy); the window fetched as aligned 128-bit vectors with the taps
+// shifted to match (9.1 ms with spills at 96 registers, 10.1 ms at 128 registers and 3 CTAs per SM); a lane = row kernel with
+// warp-uniform taps (constant bank: 45 ms, the 28 KB table thrashes the constant cache; shared memory: 9.2 ms, 16 operand
+// words per output through the LSU).
 szb_status launch_resample(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
                            uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
     if (n_clips == 0 || max_out == 0) return SZB_OK;

@@ -61,23 +61,27 @@ def summary(rep, header):
               if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and v[j]]
         for val, nm in sorted(st, reverse=True)[:8]:
             print(f"  {nm:28s} {val:6.3f}")
-    src = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "source", "--csv"))))
-    starts = [i for i, r in enumerate(src) if r and r[0] == "Address"]
-    for n, s in enumerate(starts):
-        kname = src[s - 1][1] if s >= 1 and len(src[s - 1]) > 1 else f"kernel {n}"
-        hdr = src[s]
-        end = starts[n + 1] - 1 if n + 1 < len(starts) else len(src)
+    for v in rows:
+        full = v[head.index("Kernel Name")]
+        short = full.split("(")[0].replace("void ", "").split("<")[0].strip()
+        src = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + short))))
+        starts = [i for i, r in enumerate(src) if r and r[0] == "Address"]
+        if not starts:
+            continue
+        s0 = starts[0]
+        hdr = src[s0]
+        end = starts[1] - 1 if len(starts) > 1 else len(src)
         ci, cs, cw, cx = (hdr.index(k) for k in ("Instructions Executed", "Warp Stall Sampling (All Samples)", "L1 Wavefronts Shared", "Source"))
         by, stall, wf = collections.Counter(), collections.Counter(), collections.Counter()
-        for r in src[s + 1:end]:
+        for r in src[s0 + 1:end]:
             if len(r) <= ci or not r[ci].isdigit():
                 continue
             m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[cx].strip())
             op = m.group(2) if m else r[cx].strip()
             by[op] += int(r[ci]); stall[op] += int(r[cs] or 0); wf[op] += int(r[cw] or 0)
         tot, ts = sum(by.values()), max(1, sum(stall.values()))
-        print(f"\n== dynamic instruction mix: {kname} ==\n  warp instructions {tot}, shared-memory wavefronts {sum(wf.values())}, stall samples {ts}")
-        for op, c in by.most_common(18):
+        print(f"\n== dynamic instruction mix: {short} ==\n  warp instructions {tot}, shared-memory wavefronts {sum(wf.values())}, stall samples {ts}")
+        for op, c in by.most_common(20):
             print(f"  {op:10s} {100 * c / tot:5.1f} % of instructions  {100 * stall[op] / ts:5.1f} % of stall samples")
 
 
