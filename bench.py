@@ -187,11 +187,19 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} of {N_CLIPS} clips per step, C restatement of lib.rs:186-345, one clip per thread"},
             "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print_line(line)
     return 0
 
 
 def main():
+    # Libraries print to stdout (NCCL's version banner does, on every rank): the contract is ONE JSON line there, so
+    # everything written to fd 1 during the run goes to stderr and the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global print_line
+    def print_line(obj):
+        os.write(saved, (json.dumps(obj) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -373,7 +381,7 @@ def main():
                                     "sample": f"{sample} of {n_clips} clips, C restatement of lib.rs:186-345 (oracle/oracle.c), one clip per thread, {dt:.2f} s"}
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    print_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -106,6 +106,17 @@ class Context:
         N.check(N.lib.szb_comm_init(self.handle, buf, int(rank), int(world)))
 
 
+def _ctx_peer_exchange(self, enable: bool) -> bool:
+    """Collective: switch the gradient exchange between NCCL all-reduces (default) and the fused peer-memory kernel
+    (include/streamz_b200.h, szb_comm_peer_exchange).  Returns whether the peer exchange is active."""
+    active = C.c_int32()
+    N.check(N.lib.szb_comm_peer_exchange(self.handle, 1 if enable else 0, C.byref(active)))
+    return bool(active.value)
+
+
+Context.comm_peer_exchange = _ctx_peer_exchange
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     N.check(N.lib.szb_comm_unique_id(buf))

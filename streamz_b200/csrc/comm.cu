@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -21,6 +22,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -41,6 +43,7 @@ static szb_status load_nccl() {
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
         set_error("libnccl is missing a required symbol");
@@ -91,6 +94,76 @@ szb_status comm_join(szb_ctx* ctx) {
     return SZB_OK;
 }
 
+// ---- gradient exchange over peer memory ------------------------------------------------------------------------------
+// Region layout per rank: [flags: kMaxPeers x u32, padded to 256 B][grad buffer 0: cap floats][grad buffer 1: cap floats].
+constexpr size_t kP2pCapFloats = size_t(1) << 20;   // 4 MB per buffer: nets up to ~1 M parameters (C = 1000: 420 k)
+constexpr size_t kP2pFlagBytes = 256;
+
+static void p2p_teardown(szb_ctx* ctx) {
+    for (int r = 0; r < ctx->world && r < szb_ctx::kMaxPeers; ++r) {
+        if (r != ctx->rank && ctx->p2p_flags[r]) cudaIpcCloseMemHandle(ctx->p2p_flags[r]);
+        ctx->p2p_flags[r] = nullptr;
+        ctx->p2p_grad[r] = nullptr;
+    }
+    if (ctx->p2p_region) cudaFree(ctx->p2p_region);
+    ctx->p2p_region = nullptr;
+    ctx->p2p_on = false;
+    ctx->p2p_cap = 0;
+}
+
+// Maps every rank's region into this process.  Any failure on any rank leaves ALL ranks on the NCCL path (the outcome is
+// agreed with a min all-reduce), so the ranks never disagree about which exchange a step uses.
+static szb_status p2p_setup(szb_ctx* ctx) {
+    const int W = ctx->world, me = ctx->rank;
+    int ok = (W <= szb_ctx::kMaxPeers && g_nccl.AllGather) ? 1 : 0;
+    const size_t bytes = kP2pFlagBytes + 2 * kP2pCapFloats * sizeof(float);
+    cudaIpcMemHandle_t mine{};
+    if (ok && cudaMalloc(&ctx->p2p_region, bytes) != cudaSuccess) { ctx->p2p_region = nullptr; ok = 0; }
+    if (ok && cudaMemset(ctx->p2p_region, 0, bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->p2p_region) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // exchange the handles (and the ok flags) through NCCL itself: no extra plumbing between the processes
+    struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+    static_assert(sizeof(Msg) == 128, "Msg size");
+    Msg msg{}; msg.h = mine; msg.ok = ok;
+    Msg* d_all = nullptr;
+    SZB_CUDA(cudaMalloc(&d_all, sizeof(Msg) * size_t(W + 1)));
+    SZB_CUDA(cudaMemcpy(d_all + W, &msg, sizeof msg, cudaMemcpyHostToDevice));
+    if (g_nccl.AllGather) {
+        SZB_NCCL(g_nccl.AllGather(d_all + W, d_all, sizeof(Msg), /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream));
+    }
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<Msg> all(static_cast<size_t>(W));
+    SZB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Msg) * size_t(W), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < W; ++r) ok = ok && all[size_t(r)].ok;
+    if (ok) {
+        for (int r = 0; r < W && ok; ++r) {
+            void* base = ctx->p2p_region;
+            if (r != me && cudaIpcOpenMemHandle(&base, all[size_t(r)].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            ctx->p2p_flags[r] = static_cast<uint32_t*>(base);
+            ctx->p2p_grad[r] = reinterpret_cast<float*>(static_cast<char*>(base) + kP2pFlagBytes);
+        }
+        cudaGetLastError();
+    }
+    // agree on the outcome
+    float* d_ok = reinterpret_cast<float*>(d_all);
+    const float f_ok = ok ? 1.f : 0.f;
+    SZB_CUDA(cudaMemcpy(d_ok, &f_ok, sizeof f_ok, cudaMemcpyHostToDevice));
+    SZB_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, /*ncclFloat32*/ 7, /*ncclMin*/ 3, ctx->nccl_comm, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float agreed = 0.f;
+    SZB_CUDA(cudaMemcpy(&agreed, d_ok, sizeof agreed, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    if (agreed < 0.5f) {
+        p2p_teardown(ctx);
+        return SZB_OK;
+    }
+    ctx->p2p_on = true;
+    ctx->p2p_cap = kP2pCapFloats;
+    ctx->p2p_step = 0;
+    return SZB_OK;
+}
+
 }  // namespace szb
 
 using namespace szb;
@@ -119,10 +192,35 @@ szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int3
     return SZB_OK;
 }
 
+szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active) {
+    SZB_REQUIRE(ctx, "szb_comm_peer_exchange: ctx is NULL");
+    if (ctx->world > 1 && ctx->nccl_comm) {
+        SZB_CUDA(cudaSetDevice(ctx->device));
+        if (enable && !ctx->p2p_on) SZB_TRY(p2p_setup(ctx));
+        if (!enable && ctx->p2p_on) {
+            cudaStreamSynchronize(ctx->stream);
+            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + szb_ctx::kMaxPeers;
+            SZB_NCCL(g_nccl.AllReduce(d, d, 1, 7, 0, ctx->nccl_comm, ctx->stream));   // peers may still be reading
+            SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+            p2p_teardown(ctx);
+        }
+    }
+    if (active) *active = ctx->p2p_on ? 1 : 0;
+    return SZB_OK;
+}
+
 szb_status szb_comm_destroy(szb_ctx* ctx) {
     if (!ctx) return SZB_OK;
     if (ctx->nccl_comm && g_nccl.CommDestroy) {
         cudaSetDevice(ctx->device);
+        if (ctx->p2p_on) {
+            // peers may still be reading this rank's gradients: rendezvous before the region goes away
+            cudaStreamSynchronize(ctx->stream);
+            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + szb_ctx::kMaxPeers;   // spare words of the flag block
+            g_nccl.AllReduce(d, d, 1, 7, 0, ctx->nccl_comm, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        p2p_teardown(ctx);
         g_nccl.CommDestroy(ctx->nccl_comm);
     }
     ctx->nccl_comm = nullptr;

@@ -79,4 +79,14 @@ struct szb_ctx {
     cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the rest of the backward pass
     cudaEvent_t ev_comm = nullptr;
     int rank = 0, world = 1;
+    // Gradient exchange over NVLink peer memory (comm.cu): every rank's [2][p2p_cap] gradient buffers and flag words are
+    // mapped into every other rank with CUDA IPC, and sgd_p2p_kernel (mlp.cu) reduces the peers' gradients and applies the
+    // update in ONE kernel -- no NCCL call inside a training step.  Off (NCCL all-reduce) when IPC / peer access is missing.
+    static constexpr int kMaxPeers = 16;
+    bool p2p_on = false;
+    size_t p2p_cap = 0;                       // floats per gradient buffer
+    uint32_t p2p_step = 0;                    // steps exchanged so far (flag value of the next step = p2p_step + 1)
+    float* p2p_grad[kMaxPeers] = {};          // gradient double buffer of every rank ([rank] is local memory)
+    uint32_t* p2p_flags[kMaxPeers] = {};      // flag words of every rank: p2p_flags[r][s] = last step rank s has published to r
+    void* p2p_region = nullptr;               // local allocation backing p2p_grad[rank] and p2p_flags[rank]
 };

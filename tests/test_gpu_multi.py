@@ -37,11 +37,19 @@ def _worker(rank, world, port, tmp):
         local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
         loss, used = sz.train_epoch_steps(net, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
         tot += loss; cnt += used
+    # the same two epochs again with the fused peer-memory exchange (one kernel: flags + peer loads + SGD) instead of NCCL
+    peer = ctx.comm_peer_exchange(True)
+    net2 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx)
+    for epoch in range(2):
+        local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
+        sz.train_epoch_steps(net2, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
+    w2 = net2.weights()
+    ctx.comm_peer_exchange(False)
     # extraction: each rank takes its clip range, no collective
     clips = [d[f"clip{i}"] for i in range(6)]
     lo, hi = shard_clips([len(c) for c in clips], world)[rank]
     feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
-    np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+    np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
     dist.destroy_process_group()
 
 
@@ -72,6 +80,10 @@ def test_two_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_p
         assert int(outs[k]["used"]) == cnt and abs(float(outs[k]["loss"]) - tot) <= 1e-3 * abs(tot)
         for i, w in enumerate(net.weights()):
             assert np.abs(outs[k][f"arr_{i}"] - w).max() <= 1e-5          # both replicas == the single-GPU result
+            assert bool(outs[k]["peer"])                                  # B200 boxes have NVLink peer access
+            assert np.abs(outs[k][f"q{i}"] - w).max() <= 1e-5             # ... with either gradient exchange
+    for i in range(6):
+        assert np.array_equal(outs[0][f"q{i}"], outs[1][f"q{i}"])         # rank-ordered sums: bit-identical replicas
     single = sz.FeatureExtractor(ctx).extract_batch(clips)
     seen = 0
     for k in range(2):
