@@ -575,6 +575,82 @@ def identify_speaker_cosine_emb(emb, speaker_embeds, threshold: float):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# CLI orchestration (main.rs:517-519, 651-668, 750-835), restated on the oracle's primitives
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def burn_in_limit(dataset_size: int) -> int:
+    """main.rs:517-519: ceil(n * DEFAULT_BURN_IN_FRAC) clamped to [10, 50]."""
+    return int(min(50, max(10, np.ceil(np.float32(dataset_size) * np.float32(0.2)))))
+
+
+def average_vectors(vectors) -> np.ndarray:
+    """lib.rs:144-159."""
+    acc = np.zeros_like(np.asarray(vectors[0]))
+    for v in vectors:
+        acc = acc + np.asarray(v)
+    return normalize(acc / acc.dtype.type(len(vectors)))
+
+
+def pretrain_from_features(net: Net, windows: np.ndarray, target_class: int, epochs: int, lr: float, dropout: float, batch: int,
+                           seed: int) -> float:
+    """lib.rs:582-628 with the randomness of the library's Python mirror: shuffles from default_rng(seed), dropout from the
+    counter RNG keyed (seed, epoch).  Mean loss over the surviving windows of all epochs."""
+    n = len(windows)
+    if n == 0 or epochs == 0:
+        return 0.0
+    rng = np.random.default_rng(seed)
+    labels = np.full(n, int(target_class))
+    total, count = 0.0, 0
+    for e in range(epochs):
+        perm = rng.permutation(n)
+        keep = dropout_keep_mask(seed, e, np.arange(n), windows.shape[1], dropout)
+        l, c = train_epoch(net, windows, labels, perm, batch, lr, keep)
+        total += l
+        count += c
+    return total / count if count else 0.0
+
+
+def add_output_class(net: Net, column: np.ndarray) -> int:
+    """lib.rs:797-821 with the new column given (the reference draws it from thread_rng); the new bias is 0."""
+    net.w3 = np.concatenate([net.w3, np.asarray(column, net.dtype).reshape(-1, 1)], axis=1)
+    net.b3 = np.concatenate([net.b3, np.zeros(1, net.dtype)])
+    return net.n_out - 1
+
+
+def incremental_training(net: Net, train_files: list, feature_map: dict, limit: int, conf_threshold: float, dropout: float,
+                         batch: int, epochs: int, seed: int, new_columns) -> dict:
+    """main.rs:750-835 in list order: embedding of the file, burn-in / labelled / matched speaker assignment with class
+    growth, `epochs` epochs on the file's windows at lr 0.05 (0.01 after 1000 files), running per-speaker mean embeddings."""
+    cols = iter(new_columns)
+    speaker_features, embeds, log = {}, {}, []
+    total_loss, count = 0.0, 0
+    for entry in train_files:
+        path, cls = entry[0], entry[1]
+        windows = feature_map.get(path)
+        if windows is None or len(windows) < 5:                  # main.rs:756-760, 829
+            continue
+        emb = normalize(embedding_mean(net, windows))            # main.rs:763-767
+        burn = count < limit
+        threshold = 0.5 if burn else conf_threshold
+        if burn and cls is None:                                 # main.rs:778-785
+            speaker = add_output_class(net, next(cols))
+        elif cls is not None:
+            speaker = int(cls)
+        else:                                                    # main.rs:788-798
+            matched = identify_speaker_from_embedding(emb, embeds, threshold)
+            speaker = add_output_class(net, next(cols)) if matched is None or matched >= net.n_out else int(matched)
+        entry[1] = speaker
+        lr = 0.05 if count < 1000 else 0.01
+        total_loss += pretrain_from_features(net, windows, speaker, epochs, lr, dropout, batch, seed * 7919 + count)
+        speaker_features.setdefault(speaker, []).append(emb)
+        embeds[speaker] = average_vectors(speaker_features[speaker])
+        count += 1
+        log.append((path, speaker))
+    return {"total_loss": total_loss, "count": count, "speaker_embeddings": embeds, "log": log}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # Synthetic audio (SURVEY.md section 8(d) generator; deterministic)
 # ----------------------------------------------------------------------------------------------------------------------
 
