@@ -336,15 +336,20 @@ template <int K, int D>   // K adjacent outputs per thread, whose windows start 
 __global__ void __launch_bounds__(160, (K <= 3 ? 4 : (K <= 4 ? 3 : 2)))
 resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ out_off,
                 uint32_t n_clips, const float* __restrict__ taps, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G, uint32_t rate,
-                int16_t* __restrict__ out) {
+                uint32_t lpw, int16_t* __restrict__ out) {
     constexpr int W = kResTaps + D;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const uint32_t in_per_row = uint32_t(uint64_t(Lb) * M / L);   // exact: L divides Lb
     const uint32_t n_in_tile = kResRows * in_per_row + W;         // staged input samples per tile
     float* s_in = reinterpret_cast<float*>(rs_smem);
     int16_t* s_out = reinterpret_cast<int16_t*>(rs_smem + ((size_t(n_in_tile) * 4 + 15) & ~size_t(15)));
-    const uint32_t tid = threadIdx.x, g = tid;
-    const bool worker = g < G;
+    // Output columns are dealt to the warps `lpw` lanes at a time (the last warp takes what is left, up to 32): with
+    // lpw * K outputs spanning at most 32 input samples, the window loads of a warp touch at most 32 consecutive words --
+    // one shared-memory wavefront each.  At 32 lanes (35 words for 16 kHz) every load cost two, and the kernel sat at 82 %
+    // of the shared-memory wavefront peak.
+    const uint32_t tid = threadIdx.x, n_warps = blockDim.x >> 5;
+    const uint32_t g = (tid >> 5) * lpw + (tid & 31u);
+    const bool worker = g < G && ((tid & 31u) < lpw || (tid >> 5) == n_warps - 1);
     uint32_t q0 = 0;
     float c[K][W];
     if (worker) {
@@ -595,8 +600,12 @@ static szb_status launch_resample_t(szb_ctx* ctx, dim3 grid, uint32_t threads, s
                                     const uint64_t* d_out_off, uint32_t n_clips, uint32_t L, uint32_t M, uint32_t Lb, uint32_t G,
                                     uint32_t rate, int16_t* d_out) {
     SZB_CUDA(cudaFuncSetAttribute(resample_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // lanes per warp: the most whose K * lpw outputs read at most 32 consecutive input samples, if the row still fits
+    uint32_t lpw = uint32_t((32ull * L) / (uint64_t(K) * M));
+    const uint32_t n_warps = threads / 32;
+    if (lpw >= 32 || lpw < 24 || (n_warps - 1) * lpw + 32 < G) lpw = 32;
     resample_kernel<K, D><<<grid, threads, smem, ctx->stream>>>(d_in, d_in_off, d_out_off, n_clips, ctx->taps.as<float>(), L, M, Lb, G,
-                                                                 rate, d_out);
+                                                                 rate, lpw, d_out);
     SZB_CUDA(cudaGetLastError());
     return SZB_OK;
 }
