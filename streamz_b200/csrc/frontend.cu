@@ -330,7 +330,34 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
 // windows: one window of 16 + D samples is fetched from shared memory, and each output applies its 16 taps shifted by
 // its own offset d_k <= D inside that window (the padding taps are exact zeros, so the accumulation order and the
 // result bits are unchanged): 5.7 shared loads and 17 FMAs per output instead of 16 + 16.
-constexpr int kResRows = 32;
+constexpr int kResRows = 28;      // rows per tile: 4 CTAs of ~52 KB per SM at 16 kHz
+
+// Shared-memory layout of a resampler CTA: float input span (origin moved back by up to 7 samples so that it starts on a
+// 16-byte boundary of the clip), i16 output tile, raw i16 input span of the NEXT tile (cp.async landing zone).
+struct ResLayout { size_t n_in_tile, off_out, off_raw, total; };
+__host__ __device__ inline ResLayout res_layout(uint32_t in_per_row, uint32_t Lb, int W) {
+    ResLayout l;
+    l.n_in_tile = size_t(kResRows) * in_per_row + W;
+    l.off_out = ((l.n_in_tile + 16) * 4 + 15) & ~size_t(15);
+    l.off_raw = (l.off_out + (size_t(kResRows) * Lb + 16) * 2 + 15) & ~size_t(15);
+    l.total = l.off_raw + ((l.n_in_tile + 24) * 2 + 15) / 16 * 16;
+    return l;
+}
+
+// cp.async of the raw i16 span [i_lo & ~7, ...) of a tile into s_raw, 16 bytes at a time; bytes outside the clip are
+// zero-filled by the copy itself (src-size operand).
+__device__ __forceinline__ void res_issue(const int16_t* x, int64_t n_in, int64_t i_lo, uint32_t n_in_tile, int16_t* s_raw) {
+    const int64_t a0 = i_lo & ~int64_t(7);
+    const uint32_t n_chunks = (uint32_t(i_lo - a0) + n_in_tile + 7) / 8;
+    for (uint32_t cidx = threadIdx.x; cidx < n_chunks; cidx += blockDim.x) {
+        const int64_t gs = a0 + 8 * int64_t(cidx);
+        const bool in = gs >= 0 && gs < n_in;
+        const uint32_t bytes = in ? uint32_t(min(int64_t(16), (n_in - gs) * 2)) : 0u;
+        const uint32_t dst = uint32_t(__cvta_generic_to_shared(s_raw + 8 * cidx));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(in ? x + gs : x), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 template <int K, int D>   // K adjacent outputs per thread, whose windows start at most D input samples apart
 __global__ void __launch_bounds__(160, (K <= 3 ? 4 : (K <= 4 ? 3 : 2)))
@@ -340,9 +367,11 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
     constexpr int W = kResTaps + D;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const uint32_t in_per_row = uint32_t(uint64_t(Lb) * M / L);   // exact: L divides Lb
-    const uint32_t n_in_tile = kResRows * in_per_row + W;         // staged input samples per tile
+    const ResLayout lay = res_layout(in_per_row, Lb, W);
+    const uint32_t n_in_tile = uint32_t(lay.n_in_tile);           // staged input samples per tile
     float* s_in = reinterpret_cast<float*>(rs_smem);
-    int16_t* s_out = reinterpret_cast<int16_t*>(rs_smem + ((size_t(n_in_tile) * 4 + 15) & ~size_t(15)));
+    int16_t* s_out = reinterpret_cast<int16_t*>(rs_smem + lay.off_out);
+    int16_t* s_raw = reinterpret_cast<int16_t*>(rs_smem + lay.off_raw);
     // Output columns are dealt to the warps `lpw` lanes at a time (the last warp takes what is left, up to 32): with
     // lpw * K outputs spanning at most 32 input samples, the window loads of a warp touch at most 32 consecutive words --
     // one shared-memory wavefront each.  At 32 lanes (35 words for 16 kHz) every load cost two, and the kernel sat at 82 %
@@ -372,32 +401,57 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
         const int16_t* x = in + in_off[clip];
         int16_t* y = out + out_off[clip];
         const uint64_t n_rows = (n_out + Lb - 1) / Lb;
+        const bool vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0;    // cp.async moves 16-byte chunks
         for (uint64_t row0 = uint64_t(blockIdx.x) * kResRows; row0 < n_rows; row0 += uint64_t(gridDim.x) * kResRows) {
             // ---- stage the tile's input span as float (zeros outside the clip) ----
             const int64_t i_lo = int64_t(row0) * in_per_row - (kResTaps / 2 - 1);
-            for (uint32_t base = tid; base < n_in_tile; base += 8 * blockDim.x) {
-                int16_t v[8];                                      // 8 independent loads in flight per thread
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t i = base + u * blockDim.x;
-                    const int64_t gi = i_lo + i;
-                    v[u] = (i < n_in_tile && gi >= 0 && gi < n_in) ? __ldg(x + gi) : int16_t(0);
+            uint32_t in_shift = 0;                                 // s_in[in_shift + i] holds x[i_lo + i]
+            if (vec_in) {
+                // The raw span was requested with cp.async while the previous tile was computing (2-byte global loads waited
+                // on in the staging loop held 25 % of the stall samples): wait for it, expand it to float, and request the
+                // next tile's span before the FMA loop starts.
+                const int64_t a0 = i_lo & ~int64_t(7);            // chunk grid anchored at the (16-byte aligned) clip start
+                in_shift = uint32_t(i_lo - a0);
+                const uint32_t n_chunks = (in_shift + n_in_tile + 7) / 8;
+                if (row0 == uint64_t(blockIdx.x) * kResRows) res_issue(x, n_in, i_lo, n_in_tile, s_raw);   // first tile of the clip
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+                for (uint32_t cidx = tid; cidx < n_chunks; cidx += blockDim.x) {
+                    const uint4 raw = *reinterpret_cast<const uint4*>(s_raw + 8 * cidx);
+                    float4 lo, hi;
+                    s16x2_to_f32(raw.x, lo.x, lo.y); s16x2_to_f32(raw.y, lo.z, lo.w);
+                    s16x2_to_f32(raw.z, hi.x, hi.y); s16x2_to_f32(raw.w, hi.z, hi.w);
+                    reinterpret_cast<float4*>(s_in)[2 * cidx] = lo;
+                    reinterpret_cast<float4*>(s_in)[2 * cidx + 1] = hi;
                 }
+                __syncthreads();                                   // s_raw is free again, s_in complete
+                const uint64_t row_next = row0 + uint64_t(gridDim.x) * kResRows;
+                if (row_next < n_rows) res_issue(x, n_in, int64_t(row_next) * in_per_row - (kResTaps / 2 - 1), n_in_tile, s_raw);
+            } else {
+                for (uint32_t base = tid; base < n_in_tile; base += 8 * blockDim.x) {
+                    int16_t v[8];                                  // 8 independent loads in flight per thread
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t i = base + u * blockDim.x;
-                    if (i < n_in_tile) s_in[i] = float(v[u]);
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t i = base + u * blockDim.x;
+                        const int64_t gi = i_lo + i;
+                        v[u] = (i < n_in_tile && gi >= 0 && gi < n_in) ? __ldg(x + gi) : int16_t(0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t i = base + u * blockDim.x;
+                        if (i < n_in_tile) s_in[i] = float(v[u]);
+                    }
                 }
             }
             // outputs of the tile: [j_lo, j_hi); staged at s_out[shift + (j - j_lo)] so that global and shared addresses
             // are congruent modulo 16 bytes
             const uint64_t j_lo = row0 * Lb, j_hi = min(n_out, j_lo + uint64_t(kResRows) * Lb);
             const uint32_t shift = uint32_t((reinterpret_cast<uintptr_t>(y + j_lo) >> 1) & 7);
-            __syncthreads();
+            if (!vec_in) __syncthreads();
             if (worker) {
                 const uint32_t rows_here = uint32_t((j_hi - j_lo + Lb - 1) / Lb);
                 for (uint32_t r = 0; r < rows_here; ++r) {
-                    const float* wv = s_in + r * in_per_row + q0;
+                    const float* wv = s_in + in_shift + r * in_per_row + q0;
                     float w[W];
 #pragma unroll
                     for (int t = 0; t < W; ++t) w[t] = wv[t];
@@ -632,7 +686,7 @@ static szb_status launch_resample_k(szb_ctx* ctx, const int16_t* d_in, const uin
     const uint32_t threads = (G + 31) / 32 * 32;
     const uint32_t D = std::max<uint32_t>(1, span);
     const uint64_t in_per_row = uint64_t(Lb) * M / L;
-    const size_t smem = ((size_t(kResRows) * in_per_row + kResTaps + D) * 4 + 15) / 16 * 16 + (size_t(kResRows) * Lb + 16) * 2;
+    const size_t smem = res_layout(uint32_t(in_per_row), Lb, int(kResTaps + D)).total;
     SZB_REQUIRE(smem <= 200 * 1024, "resample: rate %u needs %zu bytes of shared memory", rate, smem);
     const uint64_t tiles = ((max_out + Lb - 1) / Lb + kResRows - 1) / kResRows;
     const uint32_t gy = std::min<uint32_t>(n_clips, 65535);
