@@ -328,6 +328,52 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
         params[i] -= grads[i] * scale;
 }
 
+// Tensor-core path: the SGD update, the refresh of the transposed weight copies the GEMMs read, and the zeroing of the
+// gradient vector for the next step in ONE pass (three launches -- sgd, transpose, 753 KB memset -- become one; the step is
+// bound by its chain of dependent launches).  Walks the weights in transposed order (coalesced writes of WT, strided but
+// L2-resident reads of P and G), then the biases.
+__global__ void sgd_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ WT, int n_in, int h1, int h2, int n_out,
+                                 size_t off_b1, size_t off_w2, size_t off_b2, size_t off_w3, size_t off_b3, size_t off_wt2,
+                                 size_t off_wt3, size_t np, int parity, float lr, double* __restrict__ stats) {
+    const float n_used = G[np + 4 * parity];
+    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nthr = size_t(gridDim.x) * blockDim.x;
+    if (tid == 0) {
+        if (stats) {
+            stats[0] += double(G[np + 4 * parity + 1]);  // loss
+            stats[1] += double(n_used);
+        }
+        G[np + 4 * (1 - parity)] = 0.f;                  // the next step's block (nobody reads it during this launch)
+        G[np + 4 * (1 - parity) + 1] = 0.f;
+    }
+    const float scale = n_used > 0.f ? lr / n_used : 0.f;   // empty batch: gradients are zero, nothing moves (lib.rs:1003-1005)
+    const size_t n1 = size_t(n_in) * h1, n2 = size_t(h1) * h2, n3 = size_t(h2) * n_out;
+    for (size_t i = tid; i < n1 + n2 + n3; i += nthr) {
+        size_t src, dst;
+        if (i < n1) {                       // i indexes wt1[n][k], n < h1, k < n_in
+            const int n = int(i / n_in), k = int(i % n_in);
+            src = size_t(k) * h1 + n; dst = i;
+        } else if (i < n1 + n2) {
+            const size_t j = i - n1;
+            const int n = int(j / h1), k = int(j % h1);
+            src = off_w2 + size_t(k) * h2 + n; dst = off_wt2 + j;
+        } else {
+            const size_t j = i - n1 - n2;
+            const int n = int(j / h2), k = int(j % h2);
+            src = off_w3 + size_t(k) * n_out + n; dst = off_wt3 + j;
+        }
+        const float p = P[src] - G[src] * scale;
+        P[src] = p;
+        WT[dst] = p;
+        G[src] = 0.f;
+    }
+    const size_t nb = size_t(h1) + h2 + n_out;
+    for (size_t i = tid; i < nb; i += nthr) {
+        const size_t idx = i < size_t(h1) ? off_b1 + i : (i < size_t(h1) + h2 ? off_b2 + (i - h1) : off_b3 + (i - h1 - h2));
+        P[idx] -= G[idx] * scale;
+        G[idx] = 0.f;
+    }
+}
+
 // Multi-GPU step: gradient all-reduce and SGD update in ONE kernel over NVLink peer memory (no NCCL call in the step).
 // Every rank's gradient vector [g | n_used, loss, ..] of this step sits in its own memory, mapped into all ranks (CUDA IPC,
 // comm.cu).  (1) publish: this rank's backward pass is complete (stream order), so one thread stores the step number into
@@ -602,7 +648,7 @@ static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, co
                                  const uint8_t* valid, float threshold, unsigned long long* hist, float* sums, float* zT = nullptr) {
     if (B <= 0) return SZB_OK;
     const int wpb = 8;
-    float* tail = net->grads.as<float>() + net->n_params();
+    float* tail = net->grads.as<float>() + net->n_params() + 4 * net->tail_parity;
     if (mode == 2 && zT && net->n_out <= 128) {   // tensor-core training path
         softmax_train_kernel<<<(B + 31) / 32, 1024, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out), labels, target_vec, valid,
                                                                           tail, zT, B);
@@ -632,7 +678,13 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     // on IPC-exported memory (measured: 105 vs 48 ms per epoch at N = 2 when they accumulate there directly).
     const bool p2p = ctx->world > 1 && ctx->p2p_on && np + kGradTail <= ctx->p2p_cap;
     float* G = net->grads.as<float>();
-    SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
+    // single-context tensor-core steps end in sgd_fused_kernel, which leaves the gradient vector zeroed for the next step
+    const bool fused = net->precision != 0 && !p2p;
+    if (!net->grads_zero || (!fused && net->tail_parity != 0)) {
+        SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
+        net->tail_parity = 0;
+    }
+    net->grads_zero = false;
     bool reduced = p2p;     // gradient slices already all-reduced (overlapped) inside the backward pass, or exchanged below
     if (B > 0) {
         const float* xb = net->xb.as<float>();
@@ -730,13 +782,26 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
         const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(ctx->sm_count)));
         sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, a, np, lr, net->stats.as<double>());
+    } else if (fused) {
+        SZB_TRY(net->wt.reserve(net->n_wt() * 4));
+        const int blocks = int(std::min<size_t>((net->n_wt() + 255) / 256, size_t(ctx->sm_count) * 4));
+        sgd_fused_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, net->wt.as<float>(), int(net->n_in), int(net->h1), int(net->h2),
+                                                          int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(),
+                                                          net->off_b3(), net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr,
+                                                          net->stats.as<double>());
     } else {
         const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
         sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
     }
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    net->wt_dirty = true;
+    if (fused) {
+        net->wt_dirty = false;
+        net->grads_zero = true;
+        net->tail_parity ^= 1;
+    } else {
+        net->wt_dirty = true;
+    }
     return SZB_OK;
 }
 
@@ -862,6 +927,8 @@ szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t
     fresh->params = DevBuf(); fresh->grads = DevBuf();
     net->n_out = C + 1;
     net->wt_dirty = true;
+    net->grads_zero = false;      // fresh, uninitialised gradient buffer
+    net->tail_parity = 0;
     net->a_z.release(); net->zT.release(); net->cap_rows = 0;
     szb_net_destroy(fresh);
     return SZB_OK;

@@ -14,6 +14,8 @@ struct szb_net {
     // activations / deltas ([features][rows]) that make every GEMM of a step "TN" (gemm_tc.cuh)
     szb::DevBuf wt, xbT, h1T, h2T, zT, d2T, d1T;
     bool wt_dirty = true;
+    bool grads_zero = false;      // the gradient vector (except the other tail block) is known to be all zeros
+    int tail_parity = 0;          // which tail block the current step accumulates [n_used, loss] into
     int precision = 1;            // 0 = FP32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = TF32 tensor cores
     uint64_t cap_rows = 0, cap_rows_t = 0;
     std::vector<std::vector<std::string>> file_lists;  // lib.rs:757, host-side only
@@ -32,6 +34,9 @@ struct szb_net {
 };
 
 namespace szb {
-constexpr size_t kGradTail = 4;  // floats appended to the gradient vector: [n_used, loss, spare, spare]
+// floats appended to the gradient vector: two [n_used, loss, spare, spare] blocks.  Steps alternate between them (tail
+// parity): the fused update kernel of a step reads its own block and zeroes the other one for the next step, so no block is
+// ever zeroed while another CTA may still be reading it.
+constexpr size_t kGradTail = 8;
 szb_status net_reserve_rows(szb_net* net, uint64_t rows);
 }  // namespace szb
