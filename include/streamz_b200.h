@@ -112,6 +112,17 @@ szb_status szb_resample_to_44100(szb_ctx* ctx, const int16_t* in, uint64_t n_in,
 szb_status szb_extract(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, float* feats, uint64_t cap_windows,
                        uint64_t* n_windows);
 
+/* Windows [w_begin, w_end) of the clip `pcm` (44.1 kHz): rows identical, bit for bit, to rows w_begin .. w_end - 1 of
+ * szb_extract on the whole clip (the delta stencil reads two more frames on either side of the range and clamps at the
+ * real clip edges only).  Only the samples those frames cover are copied to the device.  This is the unit of the
+ * multi-GPU identification sweep (BASELINE configs[4]): every rank takes a window range of the long clip
+ * and the per-class counts are added on the host.  feats: [w_end - w_begin][60]. */
+szb_status szb_extract_range(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t w_begin, uint64_t w_end, float* feats,
+                             uint64_t cap_windows);
+/* Device-output form: d_feats [w_end - w_begin][60] stays on the GPU (feeds szb_identify_counts_dev / szb_net_forward_dev). */
+szb_status szb_extract_range_dev(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t w_begin, uint64_t w_end,
+                                 float* d_feats, uint64_t cap_windows);
+
 /* Batched form of the rayon loop at main.rs:500-508 (+ batch_resample, lib.rs:541-547, when rate != 44100):
  * clip c is pcm[clip_off[c] .. clip_off[c+1]) at `rate` Hz; its windows land at feats[win_off[c] .. win_off[c+1]).
  * win_off has n_clips + 1 entries and is written by the call.  With rate != 44100 the resampler runs fused in front

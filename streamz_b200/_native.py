@@ -65,6 +65,8 @@ SIGNATURES = {
     "szb_augment_dev": (i32, [vp, vp, u64, u64, vp]),
     "szb_resample_to_44100": (i32, [vp, vp, u64, u32, vp, u64, P(u64)]),
     "szb_extract": (i32, [vp, vp, u64, vp, u64, P(u64)]),
+    "szb_extract_range": (i32, [vp, vp, u64, u64, u64, vp, u64]),
+    "szb_extract_range_dev": (i32, [vp, vp, u64, u64, u64, vp, u64]),
     "szb_extract_batch": (i32, [vp, vp, vp, u32, u32, vp, u64, vp]),
     "szb_extract_batch_dev": (i32, [vp, vp, vp, u32, u32, vp, u64, vp]),
     "szb_extract_batch_windows": (u64, [vp, u32, u32]),

@@ -199,6 +199,16 @@ class FeatureExtractor:
         assert got.value == n
         return out
 
+    def extract_range(self, samples, w_begin: int, w_end: int) -> np.ndarray:
+        """Rows ``w_begin .. w_end - 1`` of :meth:`extract` on the whole clip, bit for bit, computed from the samples those
+        windows (and the two frames either side that the delta stencil reads) cover: the per-rank unit of the multi-GPU
+        identification sweep."""
+        s = _i16(samples)
+        n = max(0, int(w_end) - int(w_begin))
+        out = np.empty((n, FEATURE_SIZE), dtype=np.float32)
+        N.check(N.lib.szb_extract_range(self.ctx.handle, N.ptr(s), len(s), int(w_begin), int(w_end), N.ptr(out), n))
+        return out
+
     def extract_batch(self, clips: Sequence[np.ndarray], rate: int = DEFAULT_SAMPLE_RATE) -> List[np.ndarray]:
         """The rayon loop of main.rs:500-508 (and batch_resample, lib.rs:541-547, when ``rate != 44100``)."""
         feats, win_off = self.extract_packed(*pack_clips(clips), rate=rate)
@@ -497,6 +507,28 @@ def identify_sums(net: SimpleNeuralNet, windows) -> np.ndarray:
     sums = np.zeros(net.output_size(), dtype=np.float32)
     N.check(N.lib.szb_identify_sums(net._h, N.ptr(w), w.shape[0], N.ptr(sums)))
     return sums
+
+
+def identify_counts_sharded(net: SimpleNeuralNet, sample, threshold: float, rank: int, world: int,
+                            extractor: Optional[FeatureExtractor] = None) -> np.ndarray:
+    """This rank's share of the histogram of identify_speaker_list (lib.rs:1389-1400) for one long clip: the clip's windows
+    are cut into `world` contiguous ranges (``sharding.shard_windows``), rank r extracts and classifies range r only, and
+    the per-class counts of all ranks ADD UP to the single-GPU histogram -- summed on the host, no collective (C <= 1000
+    integers).  ``speakers_from_counts(sum)`` then gives the list."""
+    from .sharding import shard_windows
+    extractor = extractor or FeatureExtractor(net.ctx)
+    s = _i16(sample)
+    w0, w1 = shard_windows(num_windows(len(s)), world)[rank]
+    if w1 <= w0:
+        return np.zeros(net.output_size(), dtype=np.uint64)
+    return identify_counts(net, extractor.extract_range(s, w0, w1), threshold)
+
+
+def speakers_from_counts(counts) -> List[int]:
+    """lib.rs:1402-1410: speakers with a non-zero count, by count descending, ties by ascending index (stable sort)."""
+    counts = np.asarray(counts)
+    idx = [i for i in range(len(counts)) if counts[i] > 0]
+    return sorted(idx, key=lambda i: -int(counts[i]))
 
 
 def _argmax_last(v: np.ndarray) -> int:

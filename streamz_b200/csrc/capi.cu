@@ -537,4 +537,54 @@ szb_status szb_extract(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, flo
     return SZB_OK;
 }
 
+// Shared body of szb_extract_range(_dev): stages the samples of frames [f_lo, f_hi) and runs one segment whose PCM origin
+// is the (virtual) start of the clip, so the kernel indexes hops exactly as it does for a whole clip.
+static szb_status extract_range_impl(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t w_begin, uint64_t w_end,
+                                     float* d_out) {
+    const uint64_t n_total = szb_num_windows(n_samples);
+    const uint64_t f_lo = w_begin >= 2 ? w_begin - 2 : 0, f_hi = std::min<uint64_t>(w_end + 2, n_total);
+    const uint64_t s_lo = f_lo * 400, s_hi = (f_hi - 1) * 400 + 800;         // samples the frames f_lo .. f_hi - 1 cover
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_TRY(ctx->pcm.reserve((s_hi - s_lo) * 2 + 64));
+    SZB_CUDA(cudaMemcpyAsync(ctx->pcm.ptr, pcm + s_lo, (s_hi - s_lo) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    Segment sg{};
+    sg.pcm_off = 0ull - s_lo;            // (modular) offset of the clip's sample 0 relative to the staged buffer
+    sg.out_row = 0ull - w_begin;         // row w lands at d_out[(w - w_begin) * 60]
+    sg.n_total = uint32_t(n_total);
+    sg.w_begin = uint32_t(w_begin);
+    sg.w_end = uint32_t(w_end);
+    std::vector<Segment> segs{ sg };
+    SZB_TRY(upload_segments(ctx, segs, 1));
+    // s_lo is a multiple of 400 samples = 800 bytes = 50 x 16: the staged buffer keeps the clip's 16-byte phase
+    SZB_TRY(launch_extract(ctx, ctx->pcm.as<int16_t>(), 0, 1, 0, d_out, true));
+    return SZB_OK;
+}
+
+szb_status szb_extract_range_dev(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t w_begin, uint64_t w_end,
+                                 float* d_feats, uint64_t cap_windows) {
+    SZB_REQUIRE(ctx, "szb_extract_range_dev: ctx is NULL");
+    const uint64_t n_total = szb_num_windows(n_samples);
+    SZB_REQUIRE(w_begin <= w_end && w_end <= n_total, "szb_extract_range_dev: windows [%llu, %llu) outside the clip's %llu",
+                (unsigned long long)w_begin, (unsigned long long)w_end, (unsigned long long)n_total);
+    SZB_REQUIRE(n_total < (1ull << 32), "szb_extract_range_dev: clip too long");
+    SZB_REQUIRE(cap_windows >= w_end - w_begin, "szb_extract_range_dev: capacity %llu windows < %llu",
+                (unsigned long long)cap_windows, (unsigned long long)(w_end - w_begin));
+    if (w_end == w_begin) return SZB_OK;
+    SZB_REQUIRE(pcm && d_feats, "szb_extract_range_dev: NULL buffer");
+    return extract_range_impl(ctx, pcm, n_samples, w_begin, w_end, d_feats);
+}
+
+szb_status szb_extract_range(szb_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t w_begin, uint64_t w_end, float* feats,
+                             uint64_t cap_windows) {
+    SZB_REQUIRE(ctx, "szb_extract_range: ctx is NULL");
+    const uint64_t n = w_end >= w_begin ? w_end - w_begin : 0;
+    if (n) SZB_TRY(ctx->feats.reserve(n * SZB_FEATURE_SIZE * sizeof(float)));
+    SZB_TRY(szb_extract_range_dev(ctx, pcm, n_samples, w_begin, w_end, ctx->feats.as<float>(), cap_windows));
+    if (n == 0) return SZB_OK;
+    SZB_REQUIRE(feats, "szb_extract_range: NULL buffer");
+    SZB_CUDA(cudaMemcpyAsync(feats, ctx->feats.ptr, n * SZB_FEATURE_SIZE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
+}
+
 }  // extern "C"

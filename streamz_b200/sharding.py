@@ -29,6 +29,13 @@ def shard_clips(lengths: Sequence[int], world: int) -> List[Tuple[int, int]]:
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
+def shard_windows(n_windows: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous window ranges [begin, end) per rank for ONE long clip (identification sweep, BASELINE configs[4]): the
+    ranges differ by at most one window; each rank re-reads only a two-frame halo either side of its range."""
+    n = int(n_windows)
+    return [(n * r // world, n * (r + 1) // world) for r in range(world)]
+
+
 def shard_batches(perm: np.ndarray, batch: int, rank: int, world: int) -> Tuple[np.ndarray, List[int]]:
     """Slice every global batch of `perm` for `rank`.  Returns the concatenated local order and the local batch sizes
     (one per global step, possibly 0 for a rank when the last batch is short).  Every rank gets the same number of steps."""

@@ -52,6 +52,44 @@ def test_configs1_full_size_extraction_properties(sz, ctx, oracle, native):
         assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4
 
 
+def test_configs4_identification_sweep_shards_by_window_range(sz, ctx, oracle):
+    """BASELINE configs[4]: a 60-s mixed clip (6 614 windows) cut into window ranges for 1 / 2 / 4 / 8 ranks.  Every range's
+    rows are bit-identical to the rows of the whole-clip extraction, so the per-rank histograms add up to the single-GPU one
+    and the speaker list is the same (the ranks run one after the other here; each only sees its own range + halo)."""
+    from streamz_b200.sharding import shard_windows
+    clip = np.concatenate([oracle.synth_clip(s, 60 + s, 15.0) for s in range(4)])          # four speakers x 15 s
+    ex = sz.FeatureExtractor(ctx)
+    full = ex.extract(clip)
+    assert full.shape == (6614, 60)
+    onet = oracle.Net.init(60, 512, 256, 6, seed=31)
+    net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+    # a few epochs so that the histogram is not degenerate
+    labels = (np.arange(len(full)) * 4 // len(full)).astype(np.uint32)
+    data = sz.DeviceFeatures(ctx, full, labels)
+    for e in range(2):
+        sz.train_epoch(net, data, np.random.default_rng(e).permutation(len(full)).astype(np.uint32), 64, 0.02, seed=1, stream=e)
+    data.close()
+    thr = 0.5
+    want = sz.identify_counts(net, full, thr)
+    assert want.sum() > 0
+    for world in (1, 2, 4, 8):
+        total = np.zeros_like(want)
+        for rank, (w0, w1) in enumerate(shard_windows(len(full), world)):
+            assert np.array_equal(ex.extract_range(clip, w0, w1), full[w0:w1])
+            total += sz.identify_counts_sharded(net, clip, thr, rank, world, ex)
+        assert np.array_equal(total, want)
+        assert sz.speakers_from_counts(total) == sz.identify_speaker_list(net, clip, thr, ex)
+    # edge ranges: empty, single window, the clip's first and last windows
+    assert ex.extract_range(clip, 10, 10).shape == (0, 60)
+    for w0, w1 in ((0, 1), (0, 3), (6613, 6614), (6610, 6614), (1, 2), (2, 5)):
+        assert np.array_equal(ex.extract_range(clip, w0, w1), full[w0:w1])
+    short = clip[:800 + 400 * 2]                                                            # 3 windows: every range clamps at both edges
+    fs = ex.extract(short)
+    for w0 in range(3):
+        for w1 in range(w0 + 1, 4):
+            assert np.array_equal(ex.extract_range(short, w0, w1), fs[w0:w1])
+
+
 def test_configs2_full_size_training_properties(sz, ctx, oracle):
     n, n_spk, batch = 1_000_000, 100, 4096
     r = np.random.default_rng(11)

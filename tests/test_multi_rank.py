@@ -27,6 +27,16 @@ def test_shard_clips_covers_everything_once():
     assert shard_clips([5, 5], 4)[-1][1] == 2            # more ranks than clips: some ranks get nothing
 
 
+def test_shard_windows_partitions_a_clip():
+    from streamz_b200.sharding import shard_windows
+    for n in (0, 1, 5, 550, 6614):
+        for world in (1, 2, 3, 4, 8):
+            parts = shard_windows(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
 def test_shard_batches_partitions_each_global_batch():
     from streamz_b200.sharding import shard_batches
     perm = np.random.default_rng(1).permutation(1000)
