@@ -50,6 +50,14 @@ extern "C" {
     fn szb_dev_free(ctx: *mut SzbCtx, p: *mut c_void) -> c_int;
     fn szb_memcpy_h2d(ctx: *mut SzbCtx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     fn szb_identify_sums(net: *mut SzbNet, feats: *const f32, n: u64, sums: *mut f32) -> c_int;
+    fn szb_identify_counts(net: *mut SzbNet, feats: *const f32, n: u64, thr: f32, counts: *mut u64) -> c_int;
+    fn szb_extract_range(ctx: *mut SzbCtx, pcm: *const i16, n: u64, w_begin: u64, w_end: u64, feats: *mut f32, cap: u64) -> c_int;
+    fn szb_augment(ctx: *mut SzbCtx, inp: *const i16, n: u64, seed: u64, out: *mut i16) -> c_int;
+    fn szb_net_embedding_size(net: *const SzbNet, size: *mut u32) -> c_int;
+    fn szb_net_embed(net: *mut SzbNet, x: *const f32, b: u64, relu2: i32, out: *mut f32) -> c_int;
+    fn szb_net_embedding_mean(net: *mut SzbNet, feats: *const f32, n: u64, out: *mut f32) -> c_int;
+    fn szb_net_embedding_median(net: *mut SzbNet, feats: *const f32, n: u64, relu2: i32, out: *mut f32) -> c_int;
+    fn szb_cosine_similarity(a: *const f32, b: *const f32, n: u32) -> f32;
     fn szb_identify_speaker_list(net: *mut SzbNet, pcm: *const i16, n: u64, thr: f32, out: *mut u32, cap: u32, n_out: *mut u32) -> c_int;
     fn szb_net_save(net: *mut SzbNet, path: *const c_char, sample_rate: u32, bits: u32) -> c_int;
     fn szb_net_load(ctx: *mut SzbCtx, path: *const c_char, out: *mut *mut SzbNet, sr: *mut u32, bits: *mut u32) -> c_int;
@@ -319,4 +327,96 @@ pub fn identify_speaker_list(net: &SimpleNeuralNet, sample: &[i16], threshold: f
     check(unsafe { szb_identify_speaker_list(net.net, sample.as_ptr(), sample.len() as u64, threshold, out.as_mut_ptr(), out.len() as u32, &mut n) })
         .expect("identify_speaker_list");
     out[..n as usize].iter().map(|&i| i as usize).collect()
+}
+
+// ---- embeddings, augmentation, window-range extraction ------------------------------------
+
+fn flatten(windows: &[Vec<f32>]) -> Vec<f32> {
+    windows.iter().flat_map(|v| v.iter().copied()).collect()
+}
+
+impl SimpleNeuralNet {
+    /// lib.rs:903
+    pub fn embedding_size(&self) -> usize {
+        let mut n = 0u32;
+        check(unsafe { szb_net_embedding_size(self.net, &mut n) }).expect("embedding_size");
+        n as usize
+    }
+    /// lib.rs:895-900 (ReLU, tanh)
+    pub fn embed(&self, bits: &[f32]) -> Vec<f32> {
+        let mut out = vec![0f32; self.embedding_size()];
+        check(unsafe { szb_net_embed(self.net, bits.as_ptr(), 1, 0, out.as_mut_ptr()) }).expect("embed");
+        out
+    }
+    /// lib.rs:1073-1079 (ReLU, ReLU)
+    pub fn forward_embedding(&self, input: &[f32]) -> Vec<f32> {
+        let mut out = vec![0f32; self.embedding_size()];
+        check(unsafe { szb_net_embed(self.net, input.as_ptr(), 1, 1, out.as_mut_ptr()) }).expect("forward_embedding");
+        out
+    }
+}
+
+/// lib.rs:1453-1475: mean of forward_embedding over the windows, L2-normalised
+pub fn extract_embedding_from_features(net: &SimpleNeuralNet, feats: &[Vec<f32>]) -> Vec<f32> {
+    let flat = flatten(feats);
+    let mut out = vec![0f32; net.embedding_size()];
+    check(unsafe { szb_net_embedding_mean(net.net, flat.as_ptr(), feats.len() as u64, out.as_mut_ptr()) }).expect("embedding_mean");
+    out
+}
+/// lib.rs:1478-1500: per-dimension median of forward_embedding, L2-normalised
+pub fn median_embedding_from_features(net: &SimpleNeuralNet, feats: &[Vec<f32>]) -> Vec<f32> {
+    let flat = flatten(feats);
+    let mut out = vec![0f32; net.embedding_size()];
+    check(unsafe { szb_net_embedding_median(net.net, flat.as_ptr(), feats.len() as u64, 1, out.as_mut_ptr()) }).expect("embedding_median");
+    out
+}
+/// lib.rs:1418-1450
+pub fn extract_embedding(net: &SimpleNeuralNet, sample: &[i16], extractor: &FeatureExtractor) -> Vec<f32> {
+    let feats = extractor.extract(sample);
+    let flat = flatten(&feats);
+    let mut out = vec![0f32; net.embedding_size()];
+    check(unsafe { szb_net_embedding_median(net.net, flat.as_ptr(), feats.len() as u64, 0, out.as_mut_ptr()) }).expect("extract_embedding");
+    out
+}
+/// lib.rs:1531-1540
+pub fn cosine_similarity(a: &[f32], b: &[f32]) -> f32 {
+    unsafe { szb_cosine_similarity(a.as_ptr(), b.as_ptr(), a.len().min(b.len()) as u32) }
+}
+/// lib.rs:1503-1529 (`usize::MAX` when nothing passes the threshold, which is relaxed by 0.7 below 20 speakers)
+pub fn identify_speaker_from_embedding(emb: &[f32], speaker_embeddings: &std::collections::HashMap<usize, Vec<f32>>, threshold: f32) -> usize {
+    let (mut best_sim, mut best_id) = (f32::MIN, usize::MAX);
+    for (&id, centroid) in speaker_embeddings.iter() {
+        let sim = cosine_similarity(emb, centroid);
+        if sim > best_sim {
+            best_sim = sim;
+            best_id = id;
+        }
+    }
+    let dynamic = if speaker_embeddings.len() < 20 { threshold * 0.7 } else { threshold };
+    if best_sim > dynamic { best_id } else { usize::MAX }
+}
+/// lib.rs:103-116 with the draws derived from `seed` (the reference uses thread_rng)
+pub fn augment(samples: &[i16], seed: u64) -> Vec<i16> {
+    let mut out = vec![0i16; samples.len()];
+    check(unsafe { szb_augment(ctx(), samples.as_ptr(), samples.len() as u64, seed, out.as_mut_ptr()) }).expect("augment");
+    out
+}
+
+impl FeatureExtractor {
+    /// Rows `w_begin .. w_end` of `extract`, bit for bit, from the samples that range (and its two-frame halo) covers:
+    /// the per-GPU unit of the identification sweep over one long clip (one process per GPU, counts added on the host).
+    pub fn extract_range(&self, samples: &[i16], w_begin: usize, w_end: usize) -> Vec<Vec<f32>> {
+        let n = w_end.saturating_sub(w_begin);
+        let mut flat = vec![0f32; n * FEATURE_SIZE];
+        check(unsafe { szb_extract_range(ctx(), samples.as_ptr(), samples.len() as u64, w_begin as u64, w_end as u64, flat.as_mut_ptr(), n as u64) })
+            .expect("extract_range");
+        flat.chunks(FEATURE_SIZE).map(|c| c.to_vec()).collect()
+    }
+}
+/// Per-class window counts of lib.rs:1389-1400 for already extracted windows (add the ranks' vectors, then sort as lib.rs:1402-1410).
+pub fn identify_counts(net: &SimpleNeuralNet, windows: &[Vec<f32>], threshold: f32) -> Vec<u64> {
+    let flat = flatten(windows);
+    let mut counts = vec![0u64; net.output_size()];
+    check(unsafe { szb_identify_counts(net.net, flat.as_ptr(), windows.len() as u64, threshold, counts.as_mut_ptr()) }).expect("identify_counts");
+    counts
 }
