@@ -120,6 +120,7 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     szb_ctx* ctx = new szb_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
         ctx->own_stream = false;

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/streamz_b200.h"
@@ -64,6 +65,7 @@ struct szb_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // chunk pipeline of the host entry points
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
     uint64_t launches = 0;
+    bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
     // per-launch timing of the extraction kernel (roofline figure)
     bool ktime_on = false;
     double ktime_ms = 0.0;
@@ -90,3 +92,23 @@ struct szb_ctx {
     uint32_t* p2p_flags[kMaxPeers] = {};      // flag words of every rank: p2p_flags[r][s] = last step rank s has published to r
     void* p2p_region = nullptr;               // local allocation backing p2p_grad[rank] and p2p_flags[rank]
 };
+
+namespace szb {
+// Launch on the context's stream with the programmatic-stream-serialization attribute: the kernel may be scheduled while
+// its predecessor in the stream is still draining.  ONLY for kernels that execute griddepcontrol.wait before their first
+// global-memory access (and never write anything earlier); everything else keeps the <<<>>> launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(szb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace szb

@@ -33,7 +33,7 @@ struct GemmArgs {
     float* C; int ldc;            // [M][ldc] (may be null when only CT is wanted)
     float* CT; int ldct;          // optional transposed output [N][ldct]
     const float* bias;            // [N]   (TC_BIAS*)
-    const float* aux; int ldaux;  // [M][ldaux] (TC_MUL_*)
+    const float* aux; int ldaux;  // TRANSPOSED auxiliary activation [N][ldaux] (TC_MUL_*): aux[n][m] pairs with C[m][n]
     int M, N, K;
     int k_chunk;                  // K range per blockIdx.z (multiple of BK); == K rounded up when no split
 };
@@ -93,6 +93,10 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return uint32_t(r)
 // Nearest TF32 value (10-bit mantissa, round half up in magnitude): x - tf32_hi(x) is then exact in FP32 and at most
 // 2^-11 |x|, so the three-product split carries ~2^-21 relative error per term.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u); }
+// What kind::tf32 makes of an FP32 word: the 13 low mantissa bits are not read.  The warp-specialised kernel therefore
+// leaves the raw tile in place as the hi operand and only writes lo = x - trunc(x) (exact; |lo| < 2^-10 |x|, itself read
+// truncated: x = hi + lo to 2^-20 relative) -- one 16-byte shared-memory store per chunk less than rounding hi in place.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 template <int BN, int PASSES>
 struct SmemLayout {
@@ -134,8 +138,8 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& g, uint32_t tmem_d, 
                 if (EPI == TC_BIAS) x += g.bias[n];
                 if (EPI == TC_BIAS_RELU) { x += g.bias[n]; x = x > 0.f ? x : 0.f; }                       // lib.rs:882
                 if (EPI == TC_BIAS_TANH) x = tanhf(x + g.bias[n]);                                         // lib.rs:883
-                if (EPI == TC_MUL_DTANH) { const float h = g.aux[size_t(m) * g.ldaux + n]; x *= (1.f - h * h); }   // lib.rs:1034
-                if (EPI == TC_MUL_DRELU) x = g.aux[size_t(m) * g.ldaux + n] > 0.f ? x : 0.f;               // lib.rs:1040
+                if (EPI == TC_MUL_DTANH) { const float h = g.aux[size_t(n) * g.ldaux + m]; x *= (1.f - h * h); }   // lib.rs:1034
+                if (EPI == TC_MUL_DRELU) x = g.aux[size_t(n) * g.ldaux + m] > 0.f ? x : 0.f;               // lib.rs:1040
             }
             v[j] = x;
         }
@@ -164,6 +168,129 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs& g, uint32_t tmem_d, 
     }
 }
 
+// PDL (programmatic dependent launch): every kernel of a training step releases its successor at entry and waits for its
+// predecessor right before its first global-memory access, so launch latency, TMEM allocation and barrier set-up of kernel
+// n + 1 overlap the tail of kernel n.  Both are no-ops for a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Epilogue of the warp-specialised kernel.  A warp owns 32 accumulator rows (its TMEM lane quarter) x COLS columns and
+// walks them in chunks of 32 columns:
+//   row domain (lane = row m, the tcgen05.ld 32x32b layout): bias / activation / derivative factor -- the factor comes from
+//     the TRANSPOSED activation aux[n][m], so the 32 lanes read 128 contiguous bytes -- and the transposed output CT[n][m]
+//     (again 128 contiguous bytes per store);
+//   column domain: the chunk makes one trip through a warp-private 32 x 36-float shared-memory tile and leaves as 16-byte
+//     stores (or 16-byte vector reductions for the split-K gradient GEMMs) in which 8 lanes cover 128 contiguous bytes of a
+//     row of C.  Before, a lane stored 16 bytes of its own row: 32 rows, 32 half-written sectors per instruction, which made
+//     the epilogue as long as the K loop (7-13 us per GEMM of the batch-4096 step).
+constexpr int kEpiStride = 36;                                  // floats per staged row: 16-byte aligned, conflict-free
+constexpr int kEpiWarpBytes = 32 * kEpiStride * 4;              // 4608 B per warp
+template <int COLS, int EPI>
+__device__ __forceinline__ void tc_epilogue_staged(const GemmArgs& g, uint32_t tmem_d, int m0, int n0, bool have_acc, float* stage) {
+    static_assert(COLS % 32 == 0, "a warp walks its columns in chunks of 32");
+    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+    const int mrow0 = m0 + q * 32;
+    const int m = mrow0 + lane;
+    const uint32_t lane_addr = tmem_d + (uint32_t(q * 32) << 16);
+    const bool c_vec = g.C && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < COLS; c0 += 32) {
+        if (n0 + c0 >= g.N) break;
+        uint32_t r[32];
+        if (have_acc) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(lane_addr + uint32_t(c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        // the 32 factors / biases of the chunk are requested together, before anything depends on them: as one
+        // load -> use -> store chain per element the loop paid a full L2 round trip 64 times per thread (13 us per GEMM)
+        const bool row_ok = m < g.M;
+        const bool full = (m0 + BM <= g.M) && (n0 + c0 + 32 <= g.N);      // CTA-/warp-uniform: no per-element predicates
+        float a[32];
+        if (EPI == TC_MUL_DTANH || EPI == TC_MUL_DRELU) {
+            // L1-bypassing loads: with ~200 KB of the SM's 256 KB carved out as shared memory, the remaining L1 cannot hold a
+            // line for each of the CTA's 256 outstanding 128-byte requests, and allocating loads throttle on it
+            const float* ap = g.aux + size_t(n0 + c0) * g.ldaux + m;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = __ldcg(ap + size_t(j) * g.ldaux);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (row_ok && n0 + c0 + j < g.N) ? __ldcg(ap + size_t(j) * g.ldaux) : 0.f;
+            }
+        } else if (EPI != TC_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + c0 + j;
+                a[j] = n < g.N ? __ldg(g.bias + n) : 0.f;
+            }
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (EPI == TC_BIAS) x += a[j];
+            if (EPI == TC_BIAS_RELU) { x += a[j]; x = x > 0.f ? x : 0.f; }      // lib.rs:882
+            if (EPI == TC_BIAS_TANH) x = tanhf(x + a[j]);                        // lib.rs:883
+            if (EPI == TC_MUL_DTANH) x *= (1.f - a[j] * a[j]);                   // lib.rs:1034
+            if (EPI == TC_MUL_DRELU) x = a[j] > 0.f ? x : 0.f;                   // lib.rs:1040
+            v[j] = x;
+        }
+        if (EPI != TC_ATOMIC && g.CT && row_ok) {
+            float* tp = g.CT + size_t(n0 + c0) * g.ldct + m;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tp[size_t(j) * g.ldct] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + c0 + j < g.N) tp[size_t(j) * g.ldct] = v[j];
+            }
+        }
+        if (g.C) {
+            float* mine = stage + lane * kEpiStride;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            const int cc = (lane & 7) * 4, n = n0 + c0 + cc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), mm = mrow0 + rr;
+                const float4 w = *reinterpret_cast<const float4*>(stage + rr * kEpiStride + cc);
+                if (mm < g.M && n < g.N) {
+                    float* dst = g.C + size_t(mm) * g.ldc + n;
+                    if (c_vec && n + 4 <= g.N) {
+                        if (EPI == TC_ATOMIC) red_add_v4(dst, w);
+                        else *reinterpret_cast<float4*>(dst) = w;
+                    } else {
+                        const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (n + t < g.N) {
+                                if (EPI == TC_ATOMIC) atomicAdd(dst + t, e[t]);
+                                else dst[t] = e[t];
+                            }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // One CTA = one 128 x BN tile of C (x one K split).  128 threads: all of them stage operands; one issues the MMAs;
 // in the epilogue thread t owns accumulator row t (TMEM lane t).
 template <int BN, int PASSES, int EPI>
@@ -174,7 +301,8 @@ __global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
     __shared__ uint64_t s_bar[kStages];
     __shared__ uint32_t s_tmem;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    pdl_launch_dependents();
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
@@ -193,6 +321,7 @@ __global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem;
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    pdl_wait();
 
     const bool a_vec = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     const bool b_vec = (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
@@ -289,7 +418,7 @@ __global__ void __launch_bounds__(kThreadsTc) gemm_tc_kernel(const GemmArgs g) {
 // ---- cp.async-pipelined variant (the one used whenever rows are 16-byte aligned) ---------------------------------------
 // Raw FP32 K-slabs flow global -> shared with cp.async (LDGSTS, zero-filled past the matrix edge) through a ring of
 // kAStages stages, issued two k-blocks ahead of the tensor core; each thread then turns ITS OWN sixteen 16-byte chunks
-// into the hi tile (in place) and the lo tile (3xTF32), so no barrier is needed between the copy and the split.
+// into the lo tile (3xTF32; the raw tile itself serves as hi, see tf32_trunc), so no barrier is needed between the copy and the split.
 // The copies run kDist k-blocks ahead of the tensor core through a ring of kDist + 2 stages (the slot refilled at
 // iteration kb held k-block kb - 2, whose MMAs are the ones the producers wait for anyway before reusing a lo buffer).
 // MEASURED ON B200: deepening the distance from 2 to 5 k-blocks does not move the training step (180 vs 183 us at batch
@@ -309,6 +438,21 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
+#ifdef SZB_GEMM_TRACE
+__device__ unsigned long long* g_gemm_trace = nullptr;   // tools/micro/gemm_step_bench.cu: per-CTA phase stamps (ns)
+__device__ __forceinline__ void trace_stamp(int slot) {
+    if (g_gemm_trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        g_gemm_trace[size_t(cta) * 8 + slot] = t;
+    }
+}
+#define SZB_TRACE(slot) trace_stamp(slot)
+#else
+#define SZB_TRACE(slot)
+#endif
+
 constexpr int kProducerThreads = 256;                    // warps 0-7: stage + split operands, then run the epilogue
 constexpr int kThreadsAsync = kProducerThreads + 32;      // warp 8: one elected lane issues the tcgen05.mma stream
 
@@ -318,7 +462,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Warp-specialised pipeline, no CTA-wide barrier inside the K loop:
 //   producers (256 threads): wait free[(kb+2)%4] -> cp.async k-block kb+2 -> wait own copies of k-block kb -> split into
-//                            hi (in place) / lo tiles -> fence.proxy.async -> arrive on full[kb%4]
+//                            the lo tile (raw = hi) -> fence.proxy.async -> arrive on full[kb%4]
 //   issuer (1 thread):       wait full[kb%4] -> tcgen05.mma x 4 (x3 passes) -> tcgen05.commit -> free[kb%4]
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const GemmArgs g) {
@@ -329,6 +473,8 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    SZB_TRACE(0);
+    pdl_launch_dependents();
     const uint32_t smem_base = smem_u32(tc_smem);
     if ((smem_base & 1023u) != 0) __trap();
     const uint32_t lo_base = smem_base + SL::kAStages * SL::kStageBytes;
@@ -352,6 +498,8 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem;
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    pdl_wait();          // everything above is CTA-local; from here on the kernel reads what its predecessor wrote
+    SZB_TRACE(1);
 
     if (warp < kProducerThreads / 32) {
         // ------------------------------------------------ producers ------------------------------------------------
@@ -396,8 +544,7 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
                     const uint32_t off = (u < kRa ? 0u : uint32_t(SL::kATile)) + sw128_off(lr + kRows * (u < kRa ? u : u - kRa), lc);
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
-                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(v.x - h.x), "f"(v.y - h.y), "f"(v.z - h.z),
                                  "f"(v.w - h.w)
                                  : "memory");
@@ -405,7 +552,9 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy writes -> visible to the tensor core
             mbar_arrive(&s_full[kb % kAStages]);
+            if (kb == 0) SZB_TRACE(2);
         }
+        SZB_TRACE(3);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (tid == kProducerThreads) {
         // ------------------------------------------------ MMA issuer -----------------------------------------------
@@ -437,11 +586,16 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
             mbar_wait(&s_free[last % kAStages], uint32_t((last / kAStages) & 1));   // the last commit covers the whole tile
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // two warpgroups split the columns: warps 0-3 take [0, BN/2), warps 4-7 take [BN/2, BN)
-        tc_epilogue<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0);
+        SZB_TRACE(4);
+        // two warpgroups split the columns: warps 0-3 take [0, BN/2), warps 4-7 take [BN/2, BN).  Every MMA has completed
+        // and every cp.async has landed (the MMAs consumed them), so the operand ring is free to stage the output tile.
+        tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
+                                        reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    SZB_TRACE(5);
     __syncthreads();
+    SZB_TRACE(6);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
@@ -457,11 +611,19 @@ szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
     const bool aligned = g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
     if (aligned) {
-        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_async_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLA::kTotal));
-        gemm_tc_async_kernel<BN, PASSES, EPI><<<grid, kThreadsAsync, SLA::kTotal, ctx->stream>>>(g);
+        static bool attr_set[64] = {};      // per template instantiation and device
+        if (!attr_set[ctx->device & 63]) {
+            SZB_CUDA(cudaFuncSetAttribute(gemm_tc_async_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLA::kTotal));
+            attr_set[ctx->device & 63] = true;
+        }
+        SZB_CUDA(launch_pdl(ctx, gemm_tc_async_kernel<BN, PASSES, EPI>, grid, dim3(kThreadsAsync), size_t(SLA::kTotal), g));
     } else {
-        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
-        gemm_tc_kernel<BN, PASSES, EPI><<<grid, kThreadsTc, SL::kTotal, ctx->stream>>>(g);
+        static bool attr_set[64] = {};
+        if (!attr_set[ctx->device & 63]) {
+            SZB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+            attr_set[ctx->device & 63] = true;
+        }
+        SZB_CUDA(launch_pdl(ctx, gemm_tc_kernel<BN, PASSES, EPI>, grid, dim3(kThreadsTc), size_t(SL::kTotal), g));
     }
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;

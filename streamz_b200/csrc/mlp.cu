@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(1024) softmax_train_kernel(float* __restrict__
                                                             float* __restrict__ tail, float* __restrict__ zT, int ldzT) {
     __shared__ float tile[128][33];
     __shared__ float s_loss[32], s_cnt[32];
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 32, row = row0 + wrow;
     float loss = 0.f, cnt = 0.f;
@@ -286,6 +288,8 @@ __global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_
                                   int keep_by_row /* keep indexed by window id (1) or by batch row (0) */, float prob,
                                   unsigned long long key, float* __restrict__ xb, float* __restrict__ xbT, uint32_t* __restrict__ lab,
                                   uint8_t* __restrict__ valid, float* __restrict__ h1T, int h1, float* __restrict__ h2T, int h2) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();     // before the early exit: a grid must not complete before its predecessor has
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -335,6 +339,8 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
 __global__ void sgd_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ WT, int n_in, int h1, int h2, int n_out,
                                  size_t off_b1, size_t off_w2, size_t off_b2, size_t off_w3, size_t off_b3, size_t off_wt2,
                                  size_t off_wt3, size_t np, int parity, float lr, double* __restrict__ stats) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const float n_used = G[np + 4 * parity];
     const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nthr = size_t(gridDim.x) * blockDim.x;
     if (tid == 0) {
@@ -650,9 +656,8 @@ static szb_status launch_softmax(szb_net* net, int B, int mode, float* probs, co
     const int wpb = 8;
     float* tail = net->grads.as<float>() + net->n_params() + 4 * net->tail_parity;
     if (mode == 2 && zT && net->n_out <= 128) {   // tensor-core training path
-        softmax_train_kernel<<<(B + 31) / 32, 1024, 0, net->ctx->stream>>>(net->a_z.as<float>(), B, int(net->n_out), labels, target_vec, valid,
-                                                                          tail, zT, B);
-        SZB_CUDA(cudaGetLastError());
+        SZB_CUDA(launch_pdl(net->ctx, softmax_train_kernel, dim3((B + 31) / 32), dim3(1024), 0, net->a_z.as<float>(), B, int(net->n_out),
+                            labels, target_vec, valid, tail, zT, B));
         net->ctx->launches += 1;
         return SZB_OK;
     }
@@ -709,7 +714,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             // d2 = (dZ W3^T) * (1 - H2^2)                                              (lib.rs:1034)
             g = tc::GemmArgs{};
             g.A = d3; g.lda = C; g.B = P + net->off_w3(); g.ldb = C; g.C = net->d_2.as<float>(); g.ldc = H2; g.CT = net->d2T.as<float>();
-            g.ldct = B; g.aux = net->a_h2.as<float>(); g.ldaux = H2; g.M = B; g.N = H2; g.K = C;
+            g.ldct = B; g.aux = net->h2T.as<float>(); g.ldaux = B; g.M = B; g.N = H2; g.K = C;   // factor read from H2^T: coalesced
             SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, g));
             // gW2[h1][h2] = H1^T d2                                                    (lib.rs:1035-1037)
             g = tc::GemmArgs{};
@@ -719,8 +724,9 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             if (!p2p) SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w2(), net->off_w3() - net->off_w2()));
             // d1 = (d2 W2^T) * [H1 > 0]                                                (lib.rs:1039-1040)
             g = tc::GemmArgs{};
-            g.A = net->d_2.as<float>(); g.lda = H2; g.B = P + net->off_w2(); g.ldb = H2; g.C = net->d_1.as<float>(); g.ldc = H1;
-            g.CT = net->d1T.as<float>(); g.ldct = B; g.aux = net->a_h1.as<float>(); g.ldaux = H1; g.M = B; g.N = H1; g.K = H2;
+            // only d1^T is consumed (by the layer-1 weight gradient): the row-major copy is not written
+            g.A = net->d_2.as<float>(); g.lda = H2; g.B = P + net->off_w2(); g.ldb = H2; g.C = nullptr; g.ldc = H1;
+            g.CT = net->d1T.as<float>(); g.ldct = B; g.aux = net->h1T.as<float>(); g.ldaux = B; g.M = B; g.N = H1; g.K = H2;
             SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, g));
             // gW1[n_in][h1] = X^T d1                                                   (lib.rs:1041-1043)
             g = tc::GemmArgs{};
@@ -785,10 +791,9 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     } else if (fused) {
         SZB_TRY(net->wt.reserve(net->n_wt() * 4));
         const int blocks = int(std::min<size_t>((net->n_wt() + 255) / 256, size_t(ctx->sm_count) * 4));
-        sgd_fused_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, net->wt.as<float>(), int(net->n_in), int(net->h1), int(net->h2),
-                                                          int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(),
-                                                          net->off_b3(), net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr,
-                                                          net->stats.as<double>());
+        SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
+                            int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
+                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>()));
     } else {
         const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
         sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
@@ -809,11 +814,10 @@ static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t
                               const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key) {
     if (B <= 0) return SZB_OK;
     const int wpb = 8;
-    prep_batch_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, net->ctx->stream>>>(
-        d_feats, d_labels, d_perm, B, int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
-        net->precision != 0 ? net->xbT.as<float>() : nullptr, net->lab.as<uint32_t>(), net->valid.as<uint8_t>(),
-        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2));
-    SZB_CUDA(cudaGetLastError());
+    SZB_CUDA(launch_pdl(net->ctx, prep_batch_kernel, dim3((B + wpb - 1) / wpb), dim3(wpb * 32), 0, d_feats, d_labels, d_perm, B,
+                        int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
+                        net->precision != 0 ? net->xbT.as<float>() : nullptr, net->lab.as<uint32_t>(), net->valid.as<uint8_t>(),
+                        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2)));
     net->ctx->launches += 1;
     return SZB_OK;
 }
