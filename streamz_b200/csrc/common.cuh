@@ -111,7 +111,8 @@ inline cudaError_t launch_pdl(szb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid,
     // Single-GPU steps only: with the overlapped NCCL all-reduces of a multi-GPU step, the early-launched CTAs of the next
     // GEMM take the SMs the collective's kernel would have started on, and the two ranks stall each other (measured at
     // N = 2: 132 ms per epoch with PDL against 48 ms without).
-    cfg.numAttrs = (ctx->pdl && ctx->world == 1) ? 1 : 0;
+    // (The peer-memory exchange launches no collective kernel, so it keeps PDL.)
+    cfg.numAttrs = (ctx->pdl && (ctx->world == 1 || ctx->p2p_on)) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 }  // namespace szb

@@ -349,6 +349,19 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
         params[i] -= grads[i] * scale;
 }
 
+struct P2pArgs {
+    const float* grad[szb_ctx::kMaxPeers];   // this step's gradient vector of every rank
+    uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank
+    int rank, world;
+    uint32_t step;
+};
+
+// Peer data is read with ordinary L1-bypassing loads (ld.global.cg): they are ordered after the acquire of the flags by
+// the block barrier, the owner's L2 serves them, and -- unlike volatile / strong system-scope loads, measured at ~12 us
+// per peer -- the hardware keeps all of them in flight at once.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_peer_f(const float* p) { return __ldcg(p); }
+
 // Tensor-core path: the SGD update, the refresh of the transposed weight copies the GEMMs read, and the zeroing of the
 // gradient vector for the next step in ONE pass (three launches -- sgd, transpose, 753 KB memset -- become one).
 // One block = one 32 x 32 tile of a weight matrix W[k][n]: rows of P and G are read and written as 128-byte segments
@@ -358,14 +371,46 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
 __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ WT, int n_in,
                                                         int h1, int h2, int n_out, size_t off_b1, size_t off_w2, size_t off_b2,
                                                         size_t off_w3, size_t off_b3, size_t off_wt2, size_t off_wt3, size_t np, int parity,
-                                                        float lr, double* __restrict__ stats) {
+                                                        float lr, double* __restrict__ stats, const __grid_constant__ P2pArgs a) {
     __shared__ float tile[32][33];
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    const float n_used = G[np + 4 * parity];
+    // a.world > 1: the gradient of the step is the sum over the ranks' exchange buffers (peer memory, see sgd_p2p_kernel
+    // below for the flag protocol); G is this rank's private accumulation buffer, which is only zeroed here.
+    const bool peers = a.world > 1;
+    if (peers) {
+        if (blockIdx.x == 0 && threadIdx.x < a.world) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + a.rank), "r"(a.step) : "memory");
+        }
+        if (threadIdx.x < a.world) {
+            const uint32_t* f = a.flags[a.rank] + threadIdx.x;
+            uint32_t seen = 0;
+            unsigned long long t0 = 0;
+            for (uint32_t spin = 0;; ++spin) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                if (int32_t(seen - a.step) >= 0) break;
+                __nanosleep(64);
+                if ((spin & 0xFFFFu) == 0xFFFFu) {             // a peer that is minutes late has died: never hang the GPU
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > 180ull * 1000000000ull) __trap();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    auto grad_at = [&](size_t idx) -> float {        // summed in rank order: identical bits on every rank
+        if (!peers) return G[idx];
+        float g = 0.f;
+        for (int r = 0; r < a.world; ++r) g += ld_peer_f(a.grad[r] + idx);
+        return g;
+    };
+    const float n_used = grad_at(np + 4 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (stats) {
-            stats[0] += double(G[np + 4 * parity + 1]);  // loss
+            stats[0] += double(grad_at(np + 4 * parity + 1));  // loss
             stats[1] += double(n_used);
         }
         G[np + 4 * (1 - parity)] = 0.f;                  // the next step's block (nobody reads it during this launch)
@@ -389,7 +434,7 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
             const int k = k0 + r, n = n0 + lane;
             if (k < K && n < N) {
                 const size_t idx = off_w + size_t(k) * N + n;
-                const float p = P[idx] - G[idx] * scale;
+                const float p = P[idx] - grad_at(idx) * scale;
                 P[idx] = p;
                 G[idx] = 0.f;
                 tile[r][lane] = p;
@@ -408,7 +453,7 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     const size_t bt = size_t((blockIdx.x + gridDim.x - (nblk_tiles % gridDim.x)) % gridDim.x) * blockDim.x + threadIdx.x;
     for (size_t i = bt; i < nb; i += size_t(gridDim.x) * blockDim.x) {
         const size_t idx = i < size_t(h1) ? off_b1 + i : (i < size_t(h1) + h2 ? off_b2 + (i - h1) : off_b3 + (i - h1 - h2));
-        P[idx] -= G[idx] * scale;
+        P[idx] -= grad_at(idx) * scale;
         G[idx] = 0.f;
     }
 }
@@ -422,19 +467,6 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
 // the same order on every rank, so the replicas stay bit-identical -- and applies theta -= (lr / sum n_used) * sum g.
 // The buffers alternate by step parity: a rank can only overwrite buffer b two steps later, after every peer has
 // published the step in between, i.e. has finished reading b.
-struct P2pArgs {
-    const float* grad[szb_ctx::kMaxPeers];   // this step's gradient vector of every rank
-    uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank
-    int rank, world;
-    uint32_t step;
-};
-
-// Peer data is read with ordinary L1-bypassing loads (ld.global.cg): they are ordered after the acquire of the flags by
-// the block barrier, the owner's L2 serves them, and -- unlike volatile / strong system-scope loads, measured at ~12 us
-// per peer -- the hardware keeps all of them in flight at once.
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float ld_peer_f(const float* p) { return __ldcg(p); }
-
 __global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params, const __grid_constant__ P2pArgs a, size_t n, float lr,
                                                       double* __restrict__ stats) {
     if (blockIdx.x == 0 && threadIdx.x < a.world) {
@@ -717,7 +749,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     const bool p2p = ctx->world > 1 && ctx->p2p_on && np + kGradTail <= ctx->p2p_cap;
     float* G = net->grads.as<float>();
     // single-context tensor-core steps end in sgd_fused_kernel, which leaves the gradient vector zeroed for the next step
-    const bool fused = net->precision != 0 && !p2p;
+    const bool fused = net->precision != 0;   // (with the peer exchange the same kernel also sums the ranks' gradients)
     if (!net->grads_zero || (!fused && net->tail_parity != 0)) {
         SZB_CUDA(cudaMemsetAsync(G, 0, (np + kGradTail) * sizeof(float), ctx->stream));
         net->tail_parity = 0;
@@ -810,25 +842,28 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
         }
     }
+    P2pArgs a{};
+    a.world = 1;
     if (p2p) {
         SZB_CUDA(cudaMemcpyAsync(ctx->p2p_grad[ctx->rank] + size_t(ctx->p2p_step & 1u) * ctx->p2p_cap, G, (np + kGradTail) * sizeof(float),
                                  cudaMemcpyDeviceToDevice, ctx->stream));
-        P2pArgs a{};
         for (int r = 0; r < ctx->world; ++r) {
             a.grad[r] = ctx->p2p_grad[r] + size_t(ctx->p2p_step & 1u) * ctx->p2p_cap;
             a.flags[r] = ctx->p2p_flags[r];
         }
         a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
-        const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(ctx->sm_count)));
-        sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, a, np, lr, net->stats.as<double>());
-    } else if (fused) {
+    }
+    if (fused) {
         SZB_TRY(net->wt.reserve(net->n_wt() * 4));
         const int tiles = int(((net->n_in + 31) / 32) * ((net->h1 + 31) / 32) + ((net->h1 + 31) / 32) * ((net->h2 + 31) / 32) +
                               ((net->h2 + 31) / 32) * ((net->n_out + 31) / 32));
         const int blocks = std::max(1, std::min(tiles + 1, ctx->sm_count * 4));
         SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
                             int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
-                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>()));
+                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a));
+    } else if (p2p) {
+        const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(ctx->sm_count)));
+        sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, a, np, lr, net->stats.as<double>());
     } else {
         const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
         sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());
