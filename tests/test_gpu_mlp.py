@@ -28,7 +28,8 @@ def _werr(net, onet):
 
 @pytest.mark.parametrize("mode", ["3xtf32", "fp32", "tf32"])
 @pytest.mark.parametrize("dims,B", [((60, 512, 256, 100), 300), ((60, 512, 256, 2), 64), ((60, 512, 256, 1000), 33),
-                                    ((4, 3, 2, 2), 5), ((60, 512, 256, 1), 7), ((17, 33, 65, 9), 130), ((60, 512, 256, 100), 5000)])
+                                    ((4, 3, 2, 2), 5), ((60, 512, 256, 1), 7), ((17, 33, 65, 9), 130), ((60, 512, 256, 100), 5000),
+                                    ((60, 200, 72, 10), 300)])     # 16-byte-aligned rows, ragged 32-column epilogue chunks
 def test_forward(sz, ctx, oracle, dims, B, mode):
     onet, net = _pair(sz, ctx, oracle, dims, seed=B)
     net.set_precision(mode)
@@ -55,7 +56,8 @@ def test_reference_unit_test_weights_change(sz, ctx):
 
 
 @pytest.mark.parametrize("mode", ["3xtf32", "fp32", "tf32"])
-@pytest.mark.parametrize("dims,B", [((60, 512, 256, 100), 8), ((60, 512, 256, 100), 4096), ((4, 3, 2, 2), 1), ((60, 512, 256, 3), 577)])
+@pytest.mark.parametrize("dims,B", [((60, 512, 256, 100), 8), ((60, 512, 256, 100), 4096), ((4, 3, 2, 2), 1), ((60, 512, 256, 3), 577),
+                                    ((60, 200, 72, 10), 300), ((60, 512, 256, 101), 130)])
 def test_train_batch_shared_target(sz, ctx, oracle, dims, B, mode):
     onet, net = _pair(sz, ctx, oracle, dims, seed=B)
     net.set_precision(mode)
