@@ -227,8 +227,9 @@ int32_t szb_comm_world(const szb_ctx* ctx);
 /* Alternative gradient exchange (collective call: every rank, same `enable`): every rank's gradient buffers are mapped into
  * all ranks with CUDA IPC and ONE kernel per step publishes a flag, waits for the peers, sums their gradients straight out
  * of NVLink peer memory in rank order and applies the SGD update -- no NCCL call inside a step.  Results equal the NCCL
- * path's up to float reassociation.  Off by default: measured slower than the overlapped NCCL all-reduces on 8 x B200
- * (67 vs 57 ms per 245-step epoch; DESIGN.md "Multi-GPU").  *active reports whether the mapping succeeded on all ranks. */
+ * path's up to float reassociation.  Opt-in (the set-up is itself a collective call), but the faster exchange at every size
+ * measured on 8 x B200: 126 / 134 / 175 us per batch-4096 step at N = 2 / 4 / 8 against 146 / 158 / 180 us with the
+ * overlapped NCCL all-reduces (DESIGN.md "Multi-GPU").  *active reports whether the mapping succeeded on all ranks. */
 szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active);
 
 /* ---- on-disk formats (host code) ----------------------------------------------------------------------------------- */
