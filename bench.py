@@ -164,6 +164,39 @@ def cpu_reference_rate(n_clips_sample, threads, steps=1, warmup=0, seed=1):
     return n_clips_sample * CLIP_SECONDS / dt, dt
 
 
+def cpu_mlp_rate(n_windows, speakers, batch, seed=3):
+    """train windows/s of the restated reference training loop (oracle.c so_train_epoch: per-window forward for the loss, then
+    train_batch with per-sample outer-product gradients, lib.rs:599-622, 1002-1060) on ONE host thread -- the reference trains
+    under a write lock (main.rs:803, lib.rs:710), so one thread is what it uses."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(so)
+    lib.so_train_epoch.restype = C.c_size_t
+
+    class SoNet(C.Structure):   # oracle.c so_net
+        _fields_ = [("n_in", C.c_int), ("h1", C.c_int), ("h2", C.c_int), ("n_out", C.c_int)] + [(k, C.c_void_p) for k in
+                                                                                               ("w1", "b1", "w2", "b2", "w3", "b3")]
+    r = np.random.default_rng(seed)
+    dims = (60, 512, 256, speakers)
+    arrs = [r.uniform(-.5, .5, (dims[0], dims[1])), np.zeros(dims[1]), r.uniform(-.5, .5, (dims[1], dims[2])), np.zeros(dims[2]),
+            r.uniform(-.5, .5, (dims[2], dims[3])), np.zeros(dims[3])]
+    arrs = [np.ascontiguousarray(a, np.float32) for a in arrs]
+    net = SoNet(*dims, *[a.ctypes.data for a in arrs])
+    feats = r.standard_normal((n_windows, 60)).astype(np.float32)
+    labels = r.integers(0, speakers, n_windows).astype(np.uint32)
+    perm = r.permutation(n_windows).astype(np.uint32)
+    keep = (r.random((n_windows, 60)) >= 0.2).astype(np.uint8)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    loss = C.c_double()
+    t0 = time.perf_counter()
+    used = lib.so_train_epoch(C.byref(net), P(feats), P(labels), P(perm), C.c_size_t(n_windows), C.c_size_t(batch), C.c_float(0.01),
+                              P(keep), C.byref(loss))
+    dt = time.perf_counter() - t0
+    return n_windows / dt, dt, int(used)
+
+
 def cpu_sample_for(seconds, threads, cap):
     """Number of clips whose CPU extraction takes about `seconds` on this host (probe with a few clips per thread first)."""
     probe = int(min(cap, max(16, threads * 4)))
@@ -387,6 +420,15 @@ def main():
                                     "sample": f"{sample} of {n_clips} clips, C restatement of lib.rs:186-345 (oracle/oracle.c), one clip per thread, {dt:.2f} s"}
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+        if isinstance(mlp, dict) and "error" not in mlp and rank == 0:
+            try:                                               # bounded: two batches of the configs[2] shape, one thread
+                wps, dt, used = cpu_mlp_rate(2 * MLP_BATCH, MLP_SPEAKERS, MLP_BATCH)
+                mlp["cpu_baseline"] = {"value": wps, "unit": "train windows/s", "cores": 1, "kind": "port",
+                                       "sample": f"{2 * MLP_BATCH} windows (2 steps of batch {MLP_BATCH}), C restatement of lib.rs:599-622 + "
+                                                 f"1002-1060 (oracle/oracle.c so_train_epoch), one thread as the reference trains under a "
+                                                 f"write lock, {dt:.2f} s"}
+            except Exception as e:
+                mlp["cpu_baseline"] = {"error": repr(e)}
     print_line(line)
     if world > 1:
         dist.destroy_process_group()
