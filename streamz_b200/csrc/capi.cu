@@ -121,6 +121,7 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
+    if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
         ctx->own_stream = false;

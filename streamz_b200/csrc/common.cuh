@@ -66,6 +66,7 @@ struct szb_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
     uint64_t launches = 0;
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
+    bool gemm_ta = false;   // EXPERIMENTAL (SZB_GEMM_TA=1): dense-layer GEMMs with the A operand in tensor memory (gemm_tc.cuh)
     // per-launch timing of the extraction kernel (roofline figure)
     bool ktime_on = false;
     double ktime_ms = 0.0;

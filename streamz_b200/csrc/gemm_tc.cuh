@@ -599,6 +599,211 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
+// ---- A operand in tensor memory (opt-in: szb_ctx::gemm_ta / SZB_GEMM_TA=1; validated layout: tools/micro/tmem_a_gemm.cu) ----
+// The warp-specialised kernel above is bound by shared-memory bandwidth: per 32-wide k-block a 128 x 128 tile moves 96 KB of
+// staging traffic and the tensor core reads 96 KB of operands, half of them the A slices that each of the three 3xTF32
+// products fetches again.  Here the raw A slab is staged once (coalesced cp.async, as before), then thread (row m, column
+// half h) reads ITS 16 floats of the k-block back (conflict-free: the 128-byte swizzle spreads 8 rows over 8 chunk
+// positions), and writes them -- and their lo parts -- into TMEM (lane = row, column = k, the cute::UMMA::tmem_frg layout of
+// an M = 128 A fragment) with tcgen05.st; the MMAs take A from TMEM and only B from shared memory.  A's share of the
+// shared-memory traffic falls from 96 KB per k-block (fill, split read, lo write, three MMA reads of hi/lo) to 32 KB.
+// (First version, measured: rows fetched straight from global memory into registers -- correct, but a 16-byte-per-lane
+// row gather costs 32 L1 wavefronts per instruction, as much pipe time as the shared-memory traffic it replaced.)
+template <int BN, int PASSES>
+struct SmemLayoutTa {
+    static constexpr int kATile = BM * BK * 4;                       // raw A slab: staged (coalesced cp.async), read once
+    static constexpr int kBTile = BN * BK * 4;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kDist = 2;
+    static constexpr int kStages = kDist + 2;
+    static constexpr int kLoBytes = PASSES == 3 ? 2 * kBTile : 0;    // lo tiles of B only: A's lo part goes to TMEM
+    static constexpr int kRing = kStages * kStageBytes + kLoBytes;
+    static constexpr int kTotal = kRing > 116 * 1024 ? kRing : 116 * 1024;   // > half an SM: one CTA per SM, as the grids assume
+    static constexpr int kACols = 32 * (PASSES == 3 ? 2 : 1);            // TMEM columns of one A buffer: [hi 32 | lo 32]
+    static constexpr int kTmemCols = (BN + 2 * kACols) <= 128 ? 128 : ((BN + 2 * kACols) <= 256 ? 256 : 512);
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+          "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArgs g) {
+    using SL = SmemLayoutTa<BN, PASSES>;
+    constexpr int kStages = SL::kStages, kDist = SL::kDist;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ uint64_t s_full[kStages], s_free[kStages];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SZB_TRACE(0);
+    const uint32_t smem_base = smem_u32(tc_smem);
+    if ((smem_base & 1023u) != 0) __trap();
+    const uint32_t lo_base = smem_base + kStages * SL::kStageBytes;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
+    const int n_kb = (kb1 - kb0 + BK - 1) / BK;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(SL::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], kProducerThreads);
+            mbar_init(&s_free[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem;                      // columns [0, BN): accumulator
+    const uint32_t tmem_a = s_tmem + BN;                 // then two A buffers of kACols columns
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    // Dependents are released only now, with this CTA's tensor memory allocated: the ring is small enough for CTAs of the
+    // NEXT kernel to share the SM, and if they could take the TMEM columns first, a CTA of this grid would wait in
+    // tcgen05.alloc for columns held by CTAs that wait (griddepcontrol.wait) for this grid to finish.
+    pdl_launch_dependents();
+    pdl_wait();
+    SZB_TRACE(1);
+
+    if (warp < kProducerThreads / 32) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        // A and B raw slabs: cp.async ring as in gemm_tc_async_kernel; thread <-> chunk (tid & 7) of rows (tid >> 3) + 32 u
+        constexpr int kRows = kProducerThreads / 8;
+        constexpr int kRa = BM / kRows, kRb = BN / kRows;
+        const int lr = tid >> 3, lc = tid & 7;
+        auto issue = [&](int kb) {
+            const uint32_t st = smem_base + (kb % kStages) * SL::kStageBytes;
+            const int gk = kb0 + kb * BK + lc * 4;
+            const int kleft = kb1 - gk;
+            const uint32_t kbytes = kleft >= 4 ? 16u : (kleft > 0 ? uint32_t(kleft) * 4u : 0u);
+#pragma unroll
+            for (int u = 0; u < kRa; ++u) {
+                const int r = lr + kRows * u, gr = m0 + r;
+                const bool ok = gr < g.M && kbytes > 0;
+                cp_async16(st + sw128_off(r, lc), ok ? static_cast<const void*>(g.A + size_t(gr) * g.lda + gk) : static_cast<const void*>(g.A),
+                           ok ? kbytes : 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kRb; ++u) {
+                const int r = lr + kRows * u, gr = n0 + r;
+                const bool ok = gr < g.N && kbytes > 0;
+                cp_async16(st + SL::kATile + sw128_off(r, lc),
+                           ok ? static_cast<const void*>(g.B + size_t(gr) * g.ldb + gk) : static_cast<const void*>(g.B), ok ? kbytes : 0u);
+            }
+        };
+        // A -> TMEM: thread <-> row 32 (warp & 3) + lane of the tile (its TMEM lane), chunks [4 h, 4 h + 4) of the k-block
+        const int q = warp & 3, h = warp >> 2;
+        const uint32_t a_lane = uint32_t(q * 32) << 16;
+        for (int j = 0; j < kDist; ++j) {
+            if (j < n_kb) issue(j);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
+            // MMAs of k-block kb - 2 done => ring stage (kb + kDist) % kStages, lo buffer kb % 2 and TMEM A buffer kb % 2 are free
+            if (kb >= 2) {
+                mbar_wait(&s_free[(kb - 2) % kStages], uint32_t(((kb - 2) / kStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            if (kb + kDist < n_kb) issue(kb + kDist);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kDist) : "memory");   // this thread's chunks of k-block kb have landed
+            const uint32_t st = smem_base + (kb % kStages) * SL::kStageBytes;
+            // ---- B lo split first (own chunks only, no barrier needed), so the barrier below has less to wait for
+            if (PASSES == 3) {
+                const uint32_t lo = lo_base + (kb & 1) * SL::kBTile;
+#pragma unroll
+                for (int u = 0; u < kRb; ++u) {
+                    const uint32_t off = sw128_off(lr + kRows * u, lc);
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + SL::kATile + off));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(v.x - tf32_trunc(v.x)),
+                                 "f"(v.y - tf32_trunc(v.y)), "f"(v.z - tf32_trunc(v.z)), "f"(v.w - tf32_trunc(v.w))
+                                 : "memory");
+                }
+            }
+            // ---- A -> TMEM: a row's chunks were copied by other threads: producers-only barrier, then read the own row back
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+            {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(st + sw128_off(q * 32 + lane, 4 * h + c)));
+                    hi[4 * c + 0] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+                }
+                const uint32_t abuf = tmem_a + a_lane + uint32_t((kb & 1) * SL::kACols + h * 16);
+                tmem_st16(abuf, hi);                     // kind::tf32 reads the upper 19 bits: the raw word is the hi operand
+                if (PASSES == 3) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) lo[j] = hi[j] - tf32_trunc(hi[j]);
+                    tmem_st16(abuf + 32, lo);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&s_full[kb % kStages]);
+            if (kb == 0) SZB_TRACE(2);
+        }
+        SZB_TRACE(3);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (tid == kProducerThreads) {
+        // ------------------------------------------------ MMA issuer -----------------------------------------------
+        for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(&s_full[kb % kStages], uint32_t((kb / kStages) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t db_hi = make_desc_k_sw128(smem_base + (kb % kStages) * SL::kStageBytes + SL::kATile);
+            const uint64_t db_lo = make_desc_k_sw128(lo_base + (kb & 1) * SL::kBTile);
+            const uint32_t a_hi = tmem_a + uint32_t((kb & 1) * SL::kACols), a_lo = a_hi + 32;
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+                const uint64_t adv = uint64_t((k * UK * 4) >> 4);
+                const uint32_t acol = uint32_t(k * UK);
+                const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                if (PASSES == 3) {
+                    umma_tf32_ts(tmem_d, a_lo + acol, db_hi + adv, idesc, acc0);
+                    umma_tf32_ts(tmem_d, a_hi + acol, db_lo + adv, idesc, 1u);
+                    umma_tf32_ts(tmem_d, a_hi + acol, db_hi + adv, idesc, 1u);
+                } else {
+                    umma_tf32_ts(tmem_d, a_hi + acol, db_hi + adv, idesc, acc0);
+                }
+            }
+            umma_commit(&s_free[kb % kStages]);
+        }
+    }
+    if (warp < kProducerThreads / 32) {
+        if (n_kb > 0) {
+            const int last = n_kb - 1;
+            mbar_wait(&s_free[last % kStages], uint32_t((last / kStages) & 1));
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        SZB_TRACE(4);
+        tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
+                                        reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    SZB_TRACE(5);
+    __syncthreads();
+    SZB_TRACE(6);
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(SL::kTmemCols) : "memory");
+}
+
 template <int BN, int PASSES, int EPI>
 szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
     if (g.M <= 0 || g.N <= 0) return SZB_OK;
@@ -610,7 +815,15 @@ szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.K + g.k_chunk - 1) / g.k_chunk);
     const bool aligned = g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
-    if (aligned) {
+    if (aligned && ctx->gemm_ta) {
+        using SLT = SmemLayoutTa<BN, PASSES>;
+        static bool attr_set[64] = {};
+        if (!attr_set[ctx->device & 63]) {
+            SZB_CUDA(cudaFuncSetAttribute(gemm_tc_ta_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLT::kTotal));
+            attr_set[ctx->device & 63] = true;
+        }
+        SZB_CUDA(launch_pdl(ctx, gemm_tc_ta_kernel<BN, PASSES, EPI>, grid, dim3(kThreadsAsync), size_t(SLT::kTotal), g));
+    } else if (aligned) {
         static bool attr_set[64] = {};      // per template instantiation and device
         if (!attr_set[ctx->device & 63]) {
             SZB_CUDA(cudaFuncSetAttribute(gemm_tc_async_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLA::kTotal));

@@ -5,6 +5,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DSZB_GEMM_TRACE -I streamz_b200/csrc \
 //        tools/micro/gemm_step_bench.cu -o tools/micro/gemm_step_bench
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,6 +81,7 @@ int main(int argc, char** argv) {
     const int B = 4096, I = 60, H1 = 512, H2 = 256, C = 100;
     szb_ctx ctx;
     ctx.pdl = argc > 3 ? atoi(argv[3]) != 0 : true;
+    const bool use_ta = argc > 4 && atoi(argv[4]) != 0;      // A operand in tensor memory (gemm_tc_ta_kernel)
     CK(cudaSetDevice(0));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -104,7 +106,7 @@ int main(int argc, char** argv) {
     float* d2T = dalloc(size_t(H2) * B, 1.f, 16);
     float* d1 = dalloc(size_t(B) * H1, 1.f, 17);
     float* d1T = dalloc(size_t(H1) * B, 1.f, 18);
-    float* G = dalloc(size_t(200000), 0.f, 19);
+    float* G = dalloc(size_t(300000), 0.f, 19);
 
     auto narrow_for = [&](int M, int N, int split) {
         const int tiles128 = ((M + 127) / 128) * ((N + 127) / 128) * std::max(1, split);
@@ -142,6 +144,32 @@ int main(int argc, char** argv) {
     add("x: CT ld=B+32      ", tc::TC_BIAS_RELU, d2, H2, w2, H2, nullptr, H1, big, B + 32, nullptr, 0, B, H1, H2, 1);
     add("x: no output       ", tc::TC_BIAS_RELU, d2, H2, w2, H2, nullptr, H1, nullptr, B, nullptr, 0, B, H1, H2, 1);
     const int nj = int(jobs.size());
+    if (use_ta) {
+        // correctness first: every GEMM of the step with A from shared memory and with A from tensor memory, same inputs
+        bool all_ok = true;
+        for (int k = 0; k < n_chain; ++k) {
+            const Job& j = jobs[k];
+            const size_t nc = j.g.C ? size_t(j.g.M) * j.g.ldc : 0, nt = j.g.CT ? size_t(j.g.N) * j.g.ldct : 0;
+            std::vector<float> c0(nc), c1(nc), t0(nt), t1(nt);
+            for (int pass = 0; pass < 2; ++pass) {
+                ctx.gemm_ta = pass == 1;
+                if (nc) CK(cudaMemsetAsync(j.g.C, 0, nc * 4, ctx.stream));
+                if (nt) CK(cudaMemsetAsync(j.g.CT, 0, nt * 4, ctx.stream));
+                run(&ctx, j);
+                CK(cudaStreamSynchronize(ctx.stream));
+                if (nc) CK(cudaMemcpy((pass ? c1 : c0).data(), j.g.C, nc * 4, cudaMemcpyDeviceToHost));
+                if (nt) CK(cudaMemcpy((pass ? t1 : t0).data(), j.g.CT, nt * 4, cudaMemcpyDeviceToHost));
+            }
+            double dc = 0, mc = 0, dt = 0, mt = 0;
+            for (size_t i = 0; i < nc; ++i) { dc = std::max(dc, double(std::fabs(c0[i] - c1[i]))); mc = std::max(mc, double(std::fabs(c0[i]))); }
+            for (size_t i = 0; i < nt; ++i) { dt = std::max(dt, double(std::fabs(t0[i] - t1[i]))); mt = std::max(mt, double(std::fabs(t0[i]))); }
+            const bool ok = (nc == 0 || dc <= 2e-5 * mc) && (nt == 0 || dt <= 2e-5 * mt) && (nc == 0 || mc > 0);
+            all_ok = all_ok && ok;
+            printf("check %-20s C: max|diff| %.3e of max %.3e   CT: max|diff| %.3e of max %.3e   %s\n", j.name, dc, mc, dt, mt, ok ? "ok" : "MISMATCH");
+        }
+        printf("A-in-TMEM kernel vs shared-memory kernel: %s\n", all_ok ? "all GEMMs agree" : "MISMATCH");
+        ctx.gemm_ta = true;
+    }
     std::vector<cudaEvent_t> ev(nj + 1);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     for (int w = 0; w < 3; ++w)
