@@ -8,6 +8,10 @@
 // weights and by letting the producing epilogue also write the transposed activation (see mlp.cu), so a single,
 // well-tested operand layout serves all eight products of a training step.
 //
+// Kernels in this file: gemm_tc_async_kernel (the default: warp-specialised cp.async ring, both operands from shared
+// memory), gemm_tc_ta_kernel (opt-in: A operand in tensor memory), gemm_tc_kernel (fallback for rows that are not 16-byte
+// aligned).  All three share the operand form, the 3xTF32 split and -- the first two -- the staged epilogue.
+//
 // Precision: PASSES = 1 is plain TF32 (10-bit mantissa inputs, FP32 accumulate).  PASSES = 3 is the split
 // "3xTF32" scheme: x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and C += A_lo B_hi + A_hi B_lo + A_hi B_hi,
 // which restores ~FP32 accuracy (error ~2^-21 relative per product) for parity with the reference's FP32 arithmetic.
