@@ -286,12 +286,24 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                     const float* rj = s_ring + j * kRingStride;
                     auto cl = [hi](int x) { return min(max(x, 0), hi); };
                     auto C = [rj](int g) { return rj[g & (kRing - 1)]; };
+#ifdef SZB_TAIL_INTERIOR_FAST_PATH
+                    // EXPERIMENT for the next round (not compiled by default, not yet run): away from the clip's edges no
+                    // index clamps and 5 distinct ring loads instead of 9 (same operations on the same values: same bits)
+                    if (w >= 2 && int(w) + 2 <= hi) {                              // warp-uniform
+                        const float m2 = C(int(w) - 2), m1 = C(int(w) - 1), p1 = C(int(w) + 1), p2 = C(int(w) + 2);
+                        c0 = C(int(w));
+                        d1 = (p1 - m1) * 0.5f;
+                        d2 = ((p2 - c0) * 0.5f - (c0 - m2) * 0.5f) * 0.5f;
+                    } else
+#endif
+                    {
                     const int ip = cl(int(w) + 1), im = cl(int(w) - 1);
                     c0 = C(int(w));
                     d1 = (C(ip) - C(im)) * 0.5f;                                   // lib.rs:223
                     const float dp = (C(cl(ip + 1)) - C(cl(ip - 1))) * 0.5f;       // delta at clamp(w+1)
                     const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;       // delta at clamp(w-1)
                     d2 = (dp - dm) * 0.5f;                                         // lib.rs:322
+                    }
                 }
                 float sum = c0 + d1 + d2;
 #pragma unroll
