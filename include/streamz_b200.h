@@ -193,6 +193,29 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
 szb_status szb_dropout_keep_mask(uint64_t seed, uint64_t stream, const uint64_t* rows, uint64_t n_rows, uint32_t n_in,
                                  float prob, uint8_t* keep);
 
+/* ---- raw-audio training loops (lib.rs:348-397, 668-732) ------------------------------------------ */
+/* Seed of (file, epoch) inside the two loops below; the shuffled visiting order of n rows for (seed, stream) -- Fisher-Yates
+ * from the back, j = splitmix64(key ^ i) % (i + 1), the library's stand-in for `windows.shuffle(&mut thread_rng)`
+ * (lib.rs:370, 601); lr * 0.99f32.powi(step) with powi evaluated by squaring in float32 (lib.rs:709). */
+uint64_t szb_loop_seed(uint64_t seed, uint32_t file, uint32_t epoch);
+szb_status szb_shuffle_perm(uint64_t seed, uint64_t stream, uint64_t n, uint32_t* perm);
+float szb_lr_decay(float lr, int32_t step);
+/* pretrain_network (lib.rs:348-397): `epochs` times  augment (lib.rs:368) -> extract (369) -> shuffle (370) -> chunks of
+ * `batch` with input dropout, all-zero windows skipped, loss with the pre-update weights, train_batch (371-390).  pcm is a
+ * HOST clip at 44.1 kHz; everything after its upload stays on the device.  Epoch e uses szb_loop_seed(seed, 0, e) for the
+ * augmentation draws, the shuffle and the dropout stream.  Returns the summed loss and the number of windows used
+ * (the reference returns their ratio, 0.0 when no window was used, lib.rs:392-396). */
+szb_status szb_net_pretrain_network(szb_net* net, const int16_t* pcm, uint64_t n_samples, uint32_t target_class, uint32_t epochs,
+                                    float lr, float dropout, uint32_t batch, uint64_t seed, double* loss_sum, uint64_t* n_used);
+/* train_from_files (lib.rs:668-732) on decoded, resampled clips (decode stays on the host, lib.rs:696): file f is
+ * pcm[clip_off[f] .. clip_off[f+1]) with class classes[f]; each file runs `epochs` single-epoch pretrain_network calls with
+ * lr * 0.99^step, step counting every (file, epoch) in order (lib.rs:708-709).  The reference interleaves files
+ * nondeterministically (rayon + write lock); this is the file-major serialisation.  The caller records the training files
+ * (szb_net_record_training_file, lib.rs:723) and the dataset specs (lib.rs:703-706). */
+szb_status szb_net_train_from_files(szb_net* net, const int16_t* pcm, const uint64_t* clip_off, const uint32_t* classes,
+                                    uint32_t n_files, uint32_t epochs, float lr, float dropout, uint32_t batch, uint64_t seed,
+                                    double* loss_sum, uint64_t* n_used);
+
 /* ---- aggregation (lib.rs:1285-1411) -------------------------------------------------------------------------------- */
 /* Per-class count of windows whose LAST-index argmax probability is >= threshold (lib.rs:1391-1402). */
 szb_status szb_identify_counts(szb_net* net, const float* feats, uint64_t n_windows, float threshold,
@@ -241,6 +264,18 @@ szb_status szb_npy_read_f32(const char* path, float* data, uint64_t cap_elems, u
  * w3_k b3_k (k = 1..C, one column each) speaker_i_files.  Loader also accepts the legacy dense w3 / b3 pair. */
 szb_status szb_net_save(szb_net* net, const char* path, uint32_t sample_rate, uint32_t bits);
 szb_status szb_net_load(szb_ctx* ctx, const char* path, szb_net** out, uint32_t* sample_rate, uint32_t* bits);
+/* set_embeddings / embeddings (lib.rs:869-877): per-speaker (embedding[dim], mean similarity, std similarity) triples that
+ * model.npz carries as speaker_embeddings [n][dim], speaker_mean_sims [n], speaker_std_sims [n] (lib.rs:1114-1127,
+ * 1253-1264); the CLI sets them right before saving (main.rs:845-856).  get: pass all three outputs NULL for a size query. */
+szb_status szb_net_set_embeddings(szb_net* net, const float* emb, const float* mean_sims, const float* std_sims, uint32_t n,
+                                  uint32_t dim);
+szb_status szb_net_get_embeddings(const szb_net* net, float* emb, float* mean_sims, float* std_sims, uint32_t cap_n, uint32_t* n,
+                                  uint32_t* dim);
+/* The optional hidden encoding layer w4 [rows][n] (row-major) / b4 [n] (lib.rs:752-754; npz members w4_k / b4_k,
+ * lib.rs:1099-1108, 1168-1226).  Out of scope for the hot path: carried through load -> save so a
+ * reference-written model keeps it, never evaluated.  n = 0 removes it; get with w4 = b4 = NULL is a size query. */
+szb_status szb_net_set_encoding_layer(szb_net* net, const float* w4, const float* b4, uint32_t rows, uint32_t n);
+szb_status szb_net_get_encoding_layer(const szb_net* net, float* w4, float* b4, uint64_t cap_elems, uint32_t* rows, uint32_t* n);
 
 #ifdef __cplusplus
 }

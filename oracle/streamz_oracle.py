@@ -611,6 +611,100 @@ def pretrain_from_features(net: Net, windows: np.ndarray, target_class: int, epo
     return total / count if count else 0.0
 
 
+
+# --- raw-audio training loops (lib.rs:348-397, 668-732) with this repo's seeded draws -------------------------------------
+
+
+def _sm64(x: int) -> int:
+    """splitmix64 on a Python int (scalar form of _splitmix64)."""
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def loop_seed(seed: int, file: int, epoch: int) -> int:
+    """Seed of (file, epoch) in pretrain_network / train_from_files (include/streamz_b200.h: szb_loop_seed)."""
+    return _sm64((_sm64((seed ^ 0x7EA1F11E5) & _M64) + ((file << 32) | epoch)) & _M64)
+
+
+def shuffle_perm(seed: int, stream: int, n: int) -> np.ndarray:
+    """The library's stand-in for `windows.shuffle(&mut thread_rng)` (lib.rs:370, 601): Fisher-Yates from the back with
+    j = splitmix64(key ^ i) % (i + 1), key = splitmix64(seed + stream * 0xD1B54A32D192ED03 + 0x5F)."""
+    perm = np.arange(n, dtype=np.uint32)
+    key = _sm64((seed + stream * 0xD1B54A32D192ED03 + 0x5F) & _M64)
+    for i in range(n - 1, 0, -1):
+        j = _sm64(key ^ i) % (i + 1)
+        perm[i], perm[j] = perm[j], perm[i]
+    return perm
+
+
+def lr_decay(lr: float, step: int) -> np.float32:
+    """lr * 0.99f32.powi(step) (lib.rs:709); powi by squaring in float32, as compiler-rt's __powisf2 does."""
+    a, r, b = np.float32(0.99), np.float32(1.0), int(step)
+    while True:
+        if b & 1:
+            r = np.float32(r * a)
+        b //= 2
+        if b == 0:
+            break
+        a = np.float32(a * a)
+    return np.float32(np.float32(lr) * r)
+
+
+def augment_params(seed: int, n_samples: int) -> Tuple[float, float, int]:
+    """Clip-level draws of augment (lib.rs:105-107) from `seed`: noise_level U(0, 0.005), gain U(0.95, 1.05),
+    shift in [0, min(len, 800)) -- float32 arithmetic (szb_augment_params)."""
+    k = _sm64((seed ^ 0xA06DE27) & _M64)
+    f = np.float32
+    u0 = f(_sm64(k ^ 1) >> 40) * f(2.0 ** -24)
+    u1 = f(_sm64(k ^ 2) >> 40) * f(2.0 ** -24)
+    rng_ = min(int(n_samples), WINDOW_SIZE)
+    return f(f(0.005) * u0), f(f(0.95) + f(f(0.1) * u1)), (_sm64(k ^ 3) % rng_ if rng_ else 0)
+
+
+def augment_seeded(samples: np.ndarray, seed: int) -> np.ndarray:
+    nl, gain, shift = augment_params(seed, len(samples))
+    return augment(samples, shift, gain, nl, _sm64((seed ^ 0x5EED) & _M64))
+
+
+def pretrain_epoch(net: Net, samples: np.ndarray, target_class: int, lr: float, dropout: float, batch: int, epoch_seed: int,
+                   precision: str = "f64") -> Tuple[float, int]:
+    """One epoch of lib.rs:367-390: augment -> extract -> shuffle -> dropout / skip-all-zero / loss / train_batch chunks."""
+    windows = extract(augment_seeded(samples, epoch_seed), precision).astype(np.float32)
+    n = len(windows)
+    if n == 0:
+        return 0.0, 0
+    perm = shuffle_perm(epoch_seed, 0, n)
+    keep = dropout_keep_mask(epoch_seed, 0, np.arange(n), windows.shape[1], dropout)
+    return train_epoch(net, windows, np.full(n, int(target_class)), perm, batch, lr, keep)
+
+
+def pretrain_network(net: Net, samples: np.ndarray, target_class: int, epochs: int, lr: float, dropout: float, batch: int,
+                     seed: int) -> float:
+    """lib.rs:348-397; epoch e draws everything from loop_seed(seed, 0, e).  Mean loss over the windows used (0.0 if none)."""
+    total, count = 0.0, 0
+    for e in range(int(epochs)):
+        l, c = pretrain_epoch(net, samples, target_class, lr, dropout, batch, loop_seed(seed, 0, e))
+        total += l
+        count += c
+    return total / count if count else 0.0
+
+
+def train_from_files(net: Net, clips: Sequence[np.ndarray], classes: Sequence[int], epochs: int, lr: float, dropout: float, batch: int,
+                     seed: int) -> float:
+    """lib.rs:668-732 in file-major order (the single-thread serialisation of the rayon loop): per (file, epoch) one
+    pretrain_network epoch at lr * 0.99^step, the step counting every (file, epoch) (lib.rs:708-709)."""
+    total, count, step = 0.0, 0, 0
+    for f, (clip, cls) in enumerate(zip(clips, classes)):
+        for e in range(int(epochs)):
+            l, c = pretrain_epoch(net, clip, cls, float(lr_decay(lr, step)), dropout, batch, loop_seed(seed, f, e))
+            step += 1
+            total += l
+            count += c
+    return total / count if count else 0.0
+
+
 def add_output_class(net: Net, column: np.ndarray) -> int:
     """lib.rs:797-821 with the new column given (the reference draws it from thread_rng); the new bias is 0."""
     net.w3 = np.concatenate([net.w3, np.asarray(column, net.dtype).reshape(-1, 1)], axis=1)

@@ -88,6 +88,11 @@ SIGNATURES = {
     "szb_net_train_epoch_dev": (i32, [vp, vp, vp, u64, vp, u64, u32, f32, f32, u64, u64, vp, P(f64), P(u64)]),
     "szb_net_train_epoch_steps_dev": (i32, [vp, vp, vp, u64, vp, u64, vp, u32, f32, f32, u64, u64, vp, P(f64), P(u64)]),
     "szb_dropout_keep_mask": (i32, [u64, u64, vp, u64, u32, f32, vp]),
+    "szb_loop_seed": (u64, [u64, u32, u32]),
+    "szb_shuffle_perm": (i32, [u64, u64, u64, vp]),
+    "szb_lr_decay": (f32, [f32, i32]),
+    "szb_net_pretrain_network": (i32, [vp, vp, u64, u32, u32, f32, f32, u32, u64, P(f64), P(u64)]),
+    "szb_net_train_from_files": (i32, [vp, vp, vp, vp, u32, u32, f32, f32, u32, u64, P(f64), P(u64)]),
     "szb_identify_counts": (i32, [vp, vp, u64, f32, vp]),
     "szb_identify_counts_dev": (i32, [vp, vp, u64, f32, vp]),
     "szb_identify_sums": (i32, [vp, vp, u64, vp]),
@@ -107,6 +112,10 @@ SIGNATURES = {
     "szb_npy_read_f32": (i32, [C.c_char_p, vp, u64, P(u64), P(u64)]),
     "szb_net_save": (i32, [vp, C.c_char_p, u32, u32]),
     "szb_net_load": (i32, [vp, C.c_char_p, P(vp), P(u32), P(u32)]),
+    "szb_net_set_embeddings": (i32, [vp, vp, vp, vp, u32, u32]),
+    "szb_net_get_embeddings": (i32, [vp, vp, vp, vp, u32, P(u32), P(u32)]),
+    "szb_net_set_encoding_layer": (i32, [vp, vp, vp, u32, u32]),
+    "szb_net_get_encoding_layer": (i32, [vp, vp, vp, u64, P(u32), P(u32)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

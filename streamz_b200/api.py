@@ -359,6 +359,41 @@ class SimpleNeuralNet:
                                                  C.byref(used)))
         return float(loss.value), int(used.value)
 
+    def set_embeddings(self, embeds: Sequence[Tuple[np.ndarray, float, float]]):
+        """lib.rs:869-872: (embedding, mean similarity, std similarity) per speaker; saved into model.npz."""
+        n = len(embeds)
+        e = _f32(np.stack([np.asarray(v[0], np.float32) for v in embeds])) if n else np.zeros((0, 0), np.float32)
+        m = _f32([v[1] for v in embeds])
+        sd = _f32([v[2] for v in embeds])
+        N.check(N.lib.szb_net_set_embeddings(self._h, N.ptr(e) if n else None, N.ptr(m) if n else None, N.ptr(sd) if n else None, n,
+                                             e.shape[1] if n else 0))
+
+    def embeddings(self) -> List[Tuple[np.ndarray, float, float]]:
+        """lib.rs:874-877."""
+        n, dim = C.c_uint32(), C.c_uint32()
+        N.check(N.lib.szb_net_get_embeddings(self._h, None, None, None, 0, C.byref(n), C.byref(dim)))
+        if n.value == 0:
+            return []
+        e, m, sd = np.empty((n.value, dim.value), np.float32), np.empty(n.value, np.float32), np.empty(n.value, np.float32)
+        N.check(N.lib.szb_net_get_embeddings(self._h, N.ptr(e), N.ptr(m), N.ptr(sd), n.value, C.byref(n), C.byref(dim)))
+        return [(e[i].copy(), float(m[i]), float(sd[i])) for i in range(n.value)]
+
+    def set_encoding_layer(self, w4, b4):
+        """Optional hidden encoding layer (lib.rs:752-754): carried through save / load only."""
+        b = _f32(b4)
+        w = _f32(w4).reshape(-1, max(1, len(b))) if len(b) else np.zeros((0, 0), np.float32)
+        N.check(N.lib.szb_net_set_encoding_layer(self._h, N.ptr(w) if len(b) else None, N.ptr(b) if len(b) else None,
+                                                 w.shape[0] if len(b) else 0, len(b)))
+
+    def encoding_layer(self):
+        rows, n = C.c_uint32(), C.c_uint32()
+        N.check(N.lib.szb_net_get_encoding_layer(self._h, None, None, 0, C.byref(rows), C.byref(n)))
+        if n.value == 0:
+            return None
+        w, b = np.empty((rows.value, n.value), np.float32), np.empty(n.value, np.float32)
+        N.check(N.lib.szb_net_get_encoding_layer(self._h, N.ptr(w), N.ptr(b), w.size, C.byref(rows), C.byref(n)))
+        return w, b
+
     def save(self, path: str):
         N.check(N.lib.szb_net_save(self._h, path.encode(), int(self.sample_rate), int(self.bits)))
 
@@ -460,25 +495,47 @@ def pretrain_from_features(net: SimpleNeuralNet, windows, target_class: int, num
 
 
 def pretrain_network(net: SimpleNeuralNet, samples, target_class: int, num_classes: int, epochs: int, lr: float, dropout: float,
-                     batch_size: int, extractor: FeatureExtractor, rng: Optional[np.random.Generator] = None, seed: int = 0) -> float:
-    """lib.rs:348-397: every epoch augments the clip, re-extracts its windows, shuffles and trains (augment -> extract
-    -> train all run on the GPU; the windows make one trip through the host API here)."""
-    assert num_classes == net.output_size()
-    rng = rng or np.random.default_rng(seed)
-    total, count = 0.0, 0
-    for e in range(int(epochs)):
-        windows = extractor.extract(augment(samples, seed=seed * 1000003 + e, ctx=net.ctx))     # lib.rs:368-369
-        if len(windows) == 0:
-            continue
-        data = DeviceFeatures(net.ctx, windows, np.full(len(windows), int(target_class), np.uint32))
-        try:
-            l, c = train_epoch(net, data, rng.permutation(len(windows)).astype(np.uint32), max(1, int(batch_size)), lr, dropout,
-                               seed=seed, stream=e)
-        finally:
-            data.close()
-        total += l
-        count += c
-    return total / count if count else 0.0
+                     batch_size: int, extractor: Optional[FeatureExtractor] = None, seed: int = 0) -> float:
+    """lib.rs:348-397: every epoch augments the clip, re-extracts its windows, shuffles and trains.  One C-ABI call
+    (szb_net_pretrain_network): the augmented clip, its windows and the labels stay on the GPU.  Epoch ``e`` draws its
+    augmentation, shuffle and dropout decisions from ``szb_loop_seed(seed, 0, e)``.  Returns the mean loss over the
+    windows used, 0.0 when there were none (lib.rs:392-396)."""
+    assert num_classes == net.output_size(), "num_classes must equal the net's output size (forward slices to it)"
+    s = _i16(samples)
+    loss, used = C.c_double(), C.c_uint64()
+    N.check(N.lib.szb_net_pretrain_network(net._h, N.ptr(s), len(s), int(target_class), int(epochs), float(lr), float(dropout),
+                                           max(1, int(batch_size)), int(seed) & (2 ** 64 - 1), C.byref(loss), C.byref(used)))
+    return float(loss.value) / used.value if used.value else 0.0
+
+
+def train_from_files(net: SimpleNeuralNet, files: Sequence[Tuple[str, np.ndarray, int]], num_speakers: int, epochs: int, lr: float,
+                     dropout: float, batch_size: int, extractor: Optional[FeatureExtractor] = None, seed: int = 0) -> float:
+    """lib.rs:668-732.  ``files`` holds (path, decoded 44.1 kHz mono samples, class): decoding and resampling
+    (``load_and_resample_file``, lib.rs:696) stay on the caller's side.  Every (file, epoch) is one pretrain_network epoch at
+    ``lr * 0.99**step`` (lib.rs:708-709), in file-major order -- one legal serialisation of the reference's rayon loop under
+    its write lock; training files are recorded (lib.rs:723) and the dataset specs set (lib.rs:703-706).  Returns the mean
+    loss over all windows used (the reference discards it)."""
+    assert num_speakers == net.output_size(), "num_speakers must equal the net's output size"
+    files = [(p, _i16(x), int(c)) for p, x, c in files]
+    if not files or epochs <= 0:
+        return 0.0
+    pcm, off = pack_clips([x for _, x, _ in files])
+    classes = np.array([c for _, _, c in files], dtype=np.uint32)
+    net.sample_rate, net.bits = DEFAULT_SAMPLE_RATE, 16
+    loss, used = C.c_double(), C.c_uint64()
+    N.check(N.lib.szb_net_train_from_files(net._h, N.ptr(pcm), N.ptr(off), N.ptr(classes), len(files), int(epochs), float(lr),
+                                           float(dropout), max(1, int(batch_size)), int(seed) & (2 ** 64 - 1), C.byref(loss),
+                                           C.byref(used)))
+    for path, _, cls in files:
+        net.record_training_file(cls, path)
+    return float(loss.value) / used.value if used.value else 0.0
+
+
+def shuffle_perm(seed: int, stream: int, n: int) -> np.ndarray:
+    """The library's seeded stand-in for ``windows.shuffle(&mut thread_rng)`` (lib.rs:370, 601)."""
+    perm = np.zeros(max(1, int(n)), dtype=np.uint32)
+    N.check(N.lib.szb_shuffle_perm(int(seed) & (2 ** 64 - 1), int(stream), int(n), N.ptr(perm)))
+    return perm[:n]
 
 
 def train_from_feature_map(net: SimpleNeuralNet, feature_map: Dict[str, np.ndarray], files: Iterable[Tuple[str, int]], epochs: int,

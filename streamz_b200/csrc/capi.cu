@@ -59,6 +59,36 @@ void PinnedBuf::release() {
     cap = 0;
 }
 
+szb_status StagingRing::acquire(size_t bytes, void** out) {
+    const int s = next;
+    next = (next + 1) % kSlots;
+    if (busy[s]) {
+        SZB_CUDA(cudaEventSynchronize(ev[s]));
+        busy[s] = false;
+    }
+    SZB_TRY(buf[s].reserve(bytes ? bytes : 1));
+    cur = s;
+    *out = buf[s].ptr;
+    return SZB_OK;
+}
+szb_status StagingRing::uploaded(cudaStream_t stream) {
+    if (cur < 0) return SZB_OK;
+    if (!ev[cur]) SZB_CUDA(cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming));
+    SZB_CUDA(cudaEventRecord(ev[cur], stream));
+    busy[cur] = true;
+    cur = -1;
+    return SZB_OK;
+}
+void StagingRing::release() {
+    for (int s = 0; s < kSlots; ++s) {
+        if (busy[s]) cudaEventSynchronize(ev[s]);
+        if (ev[s]) cudaEventDestroy(ev[s]);
+        ev[s] = nullptr;
+        busy[s] = false;
+        buf[s].release();
+    }
+}
+
 static szb_status drain_ktime(szb_ctx* ctx) {
     for (auto& pr : ctx->ktime_pending) {
         SZB_CUDA(cudaEventSynchronize(pr.second));
@@ -157,10 +187,9 @@ void szb_ctx_destroy(szb_ctx* ctx) {
     }
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
-                       &ctx->x })
+                       &ctx->x, &ctx->loop_pcm, &ctx->loop_labels })
         b->release();
-    ctx->h_segs.release();
-    ctx->h_misc.release();
+    ctx->h_stage.release();
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -428,13 +457,15 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     if (resample) {                   // ... or at misc[off44[c]] after the resampler
         SZB_TRY(ctx->misc.reserve(off44[n_clips] * 2 + 64));
         SZB_TRY(ctx->labels.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
-        SZB_TRY(ctx->h_misc.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
-        uint64_t* h = ctx->h_misc.as<uint64_t>();
+        void* hp = nullptr;
+        SZB_TRY(ctx->h_stage.acquire((size_t(n_clips) + 1) * 2 * sizeof(uint64_t), &hp));
+        uint64_t* h = static_cast<uint64_t*>(hp);
         for (uint32_t c = 0; c <= n_clips; ++c) {
             h[c] = clip_off[c] - first;
             h[n_clips + 1 + c] = off44[c];
         }
         SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, h, (size_t(n_clips) + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
         d_in_off = ctx->labels.as<uint64_t>();
         d_out_off = d_in_off + n_clips + 1;
         d_pcm44 = ctx->misc.as<int16_t>();

@@ -55,6 +55,22 @@ struct PinnedBuf {
     template <typename T> T* as() const { return static_cast<T*>(ptr); }
 };
 
+// Pinned staging for small host -> device uploads (segment tables, clip offsets) issued with cudaMemcpyAsync from *_dev entry
+// points that return without synchronising: a slot is only rewritten after the copy that last read it has completed (event),
+// so a second call cannot overwrite the table of a launch that is still queued.  kSlots calls may be in flight before a call
+// has to wait for the oldest upload.
+struct StagingRing {
+    static constexpr int kSlots = 8;
+    PinnedBuf buf[kSlots];
+    cudaEvent_t ev[kSlots] = {};
+    bool busy[kSlots] = {};
+    int next = 0;
+    int cur = -1;
+    szb_status acquire(size_t bytes, void** out);      // waits for the slot's previous upload, grows it, returns its pointer
+    szb_status uploaded(cudaStream_t stream);          // call right after enqueueing the copy that reads the acquired slot
+    void release();
+};
+
 }  // namespace szb
 
 struct szb_ctx {
@@ -66,7 +82,8 @@ struct szb_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
     uint64_t launches = 0;
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
-    bool gemm_ta = false;   // EXPERIMENTAL (SZB_GEMM_TA=1): dense-layer GEMMs with the A operand in tensor memory (gemm_tc.cuh)
+    bool gemm_ta = true;    // dense-layer GEMMs take the A operand from tensor memory (gemm_tc_ta_kernel); SZB_GEMM_TA=0 selects the
+                            // shared-memory-operand kernel (round 2: full GPU suite green with it, 97.1 vs 101.0 us per batch-4096 step)
     // per-launch timing of the extraction kernel (roofline figure)
     bool ktime_on = false;
     double ktime_ms = 0.0;
@@ -75,7 +92,11 @@ struct szb_ctx {
     std::vector<cudaEvent_t> pipe_events;                // chunk pipeline of szb_extract_batch
     // scratch
     szb::DevBuf segs, counter, pcm, feats, taps, labels, misc, probs, x;
-    szb::PinnedBuf h_segs, h_misc;
+    szb::StagingRing h_stage;
+    // raw-audio training loops (loops.cu): the files' PCM + one augmented clip, and a constant label column
+    szb::DevBuf loop_pcm, loop_labels;
+    uint64_t loop_labels_n = 0;
+    uint32_t loop_labels_class = 0;
     uint32_t taps_rate = 0;  // rate the taps buffer currently holds
     // NCCL (loaded lazily with dlopen; see comm.cu)
     void* nccl_comm = nullptr;

@@ -625,11 +625,13 @@ void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_
 szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint32_t n_queues) {
     SZB_TRY(ctx->segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(Segment)));
     SZB_TRY(ctx->counter.reserve(std::max<uint32_t>(1, n_queues) * sizeof(unsigned int)));
-    SZB_TRY(ctx->h_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(Segment)));
     if (!segs.empty()) {
-        std::memcpy(ctx->h_segs.ptr, segs.data(), segs.size() * sizeof(Segment));
-        SZB_CUDA(cudaMemcpyAsync(ctx->segs.ptr, ctx->h_segs.ptr, segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+        // pinned staging slot of its own per call: the copy is asynchronous and the *_dev entry points do not synchronise
+        void* hp = nullptr;
+        SZB_TRY(ctx->h_stage.acquire(segs.size() * sizeof(Segment), &hp));
+        std::memcpy(hp, segs.data(), segs.size() * sizeof(Segment));
+        SZB_CUDA(cudaMemcpyAsync(ctx->segs.ptr, hp, segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, ctx->stream));
+        SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
     }
     SZB_CUDA(cudaMemsetAsync(ctx->counter.ptr, 0, std::max<uint32_t>(1, n_queues) * sizeof(unsigned int), ctx->stream));
     return SZB_OK;

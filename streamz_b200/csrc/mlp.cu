@@ -1124,6 +1124,10 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     SZB_REQUIRE(total == n_perm, "szb_net_train_epoch_steps_dev: step sizes sum to %llu, perm has %llu rows", (unsigned long long)total,
                 (unsigned long long)n_perm);
     SZB_REQUIRE(n_perm == 0 || (d_feats && d_labels), "szb_net_train_epoch_steps_dev: NULL device buffer");
+    // the counter of the library's dropout stream packs the feature index into 6 bits (dropout_keep): wider inputs would
+    // reuse the draws of the next window.  Explicit decisions (d_keep) have no such limit.
+    SZB_REQUIRE(dropout <= 0.f || d_keep || net->n_in <= 64,
+                "szb_net_train_epoch_steps_dev: the counter dropout stream supports n_in <= 64 (net has %u); pass d_keep", net->n_in);
     for (uint64_t i = 0; i < n_perm; ++i)
         SZB_REQUIRE(perm[i] < n, "szb_net_train_epoch_steps_dev: perm[%llu] = %u out of range", (unsigned long long)i, perm[i]);
     szb_ctx* ctx = net->ctx;

@@ -19,6 +19,13 @@ struct szb_net {
     int precision = 1;            // 0 = FP32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = TF32 tensor cores
     uint64_t cap_rows = 0, cap_rows_t = 0;
     std::vector<std::vector<std::string>> file_lists;  // lib.rs:757, host-side only
+    // Saved speaker embeddings with their quality metrics (lib.rs:760-761, set_embeddings / embeddings lib.rs:870-877) and
+    // the optional hidden encoding layer (lib.rs:752-754).  Host-side state that model.npz carries (lib.rs:1099-1127,
+    // 1168-1264); the hot path never reads the encoding layer, it is kept only so that load -> save loses nothing.
+    std::vector<float> emb, emb_mean, emb_std;         // [emb_n][emb_dim], [emb_n], [emb_n]
+    uint32_t emb_n = 0, emb_dim = 0;
+    std::vector<float> w4, b4;                         // [w4_rows][b4.size()] row-major, [n]
+    uint32_t w4_rows = 0;
 
     size_t off_w1() const { return 0; }
     size_t off_b1() const { return size_t(n_in) * h1; }

@@ -180,6 +180,7 @@ def training_run(clips: Dict[str, Tuple[np.ndarray, int]], train_files: List[Lis
     init_loss = initial_training(net, feature_map, train_files, epochs=initial_epochs, seed=seed) if fresh else None
     inc = incremental_training(net, train_files, feature_map, limit, conf_threshold=conf_threshold, seed=seed)
     final = api.compute_speaker_embeddings(net, feature_map)
+    net.set_embeddings(final)                                    # main.rs:854: saved with the model (lib.rs:1114-1127)
     if model_path:
         net.save(model_path)
     return {"net": net, "feature_map": feature_map, "burn_in_limit": limit, "initial_loss": init_loss, "incremental": inc,

@@ -94,3 +94,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "streamz_oracle" not in text.replace("oracle/streamz_oracle.py", "") and "liboracle" not in text, f
+
+
+def test_seeded_loop_draws_match_the_oracle(native, oracle):
+    """Host-side draws of the raw-audio training loops (szb_loop_seed, szb_shuffle_perm, szb_lr_decay, szb_augment_params):
+    the library and the oracle must agree bit for bit, or the GPU parity tests of pretrain_network / train_from_files
+    (lib.rs:348-397, 668-732) would compare different runs.  No GPU needed: these are plain host functions."""
+    import ctypes as C
+    for n in (0, 1, 2, 17, 550):
+        p = np.zeros(max(1, n), np.uint32)
+        native.check(native.lib.szb_shuffle_perm(9, 3, n, native.ptr(p)))
+        assert np.array_equal(p[:n], oracle.shuffle_perm(9, 3, n))
+        assert sorted(p[:n].tolist()) == list(range(n))
+    for step in range(0, 80, 7):
+        assert np.float32(native.lib.szb_lr_decay(0.01, step)) == oracle.lr_decay(0.01, step)
+    assert abs(float(oracle.lr_decay(0.01, 50)) - 0.01 * 0.99 ** 50) < 1e-8
+    for args in [(0, 0, 0), (1, 2, 3), (2 ** 63 + 5, 7, 99)]:
+        assert native.lib.szb_loop_seed(*args) == oracle.loop_seed(*args)
+    nl, g, sh = C.c_float(), C.c_float(), C.c_uint64()
+    for seed in (0, 5, oracle.loop_seed(3, 1, 2)):
+        for n in (22050, 300, 0):
+            native.check(native.lib.szb_augment_params(seed, n, C.byref(nl), C.byref(g), C.byref(sh)))
+            o = oracle.augment_params(seed, n)
+            assert (np.float32(nl.value), np.float32(g.value), sh.value) == (o[0], o[1], o[2])

@@ -166,12 +166,62 @@ def test_augment_is_integer_exact(sz, ctx, oracle, native):
     assert sz.augment(loud, 4, ctx).max() <= 32767 and sz.augment(-loud - 1, 4, ctx).min() >= -32768
 
 
-def test_pretrain_network_runs_augment_extract_train(sz, ctx, oracle):
-    # lib.rs:348-397: per epoch augment -> extract -> shuffle -> train
+def test_pretrain_network_equals_the_oracle_loop(sz, ctx, oracle):
+    # lib.rs:348-397 with every draw seeded (szb_loop_seed): augment -> extract -> shuffle -> dropout -> train_batch chunks.
+    # Same augmented samples (integer-exact), same order, same dropout decisions => weights within 1e-4 of the float32 oracle.
+    clip = oracle.synth_clip(1, 21, 0.35)                         # 37 windows: 5 steps of batch 8 per epoch
+    onet = oracle.Net.init(60, 512, 256, 3, seed=11)
+    net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+    got = sz.pretrain_network(net, clip, 2, 3, 2, 0.01, 0.2, 8, seed=17)
+    want = oracle.pretrain_network(onet, clip, 2, 2, 0.01, 0.2, 8, seed=17)
+    err = max(float(np.abs(a - b).max()) for a, b in zip(net.weights(), onet.params()))
+    assert err <= 1e-4, err
+    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
+    assert sz.pretrain_network(net, clip[:500], 0, 3, 2, 0.01, 0.2, 8) == 0.0        # no windows -> 0.0 (lib.rs:392-396)
+
+
+def test_train_from_files_equals_the_oracle_loop(sz, ctx, oracle):
+    # lib.rs:668-732: per (file, epoch) one pretrain_network epoch at lr * 0.99^step; file-major order
+    clips = [oracle.synth_clip(0, 31, 0.30), oracle.synth_clip(1, 32, 0.26), np.zeros(300, np.int16), oracle.synth_clip(0, 33, 0.22)]
+    classes = [0, 1, 1, 0]
+    onet = oracle.Net.init(60, 512, 256, 2, seed=12)
+    net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+    files = [(f"spk/{i}.wav", c, k) for i, (c, k) in enumerate(zip(clips, classes))]
+    got = sz.train_from_files(net, files, 2, 2, 0.05, 0.2, 8, seed=5)
+    want = oracle.train_from_files(onet, clips, classes, 2, 0.05, 0.2, 8, seed=5)
+    err = max(float(np.abs(a - b).max()) for a, b in zip(net.weights(), onet.params()))
+    assert err <= 1e-4, err
+    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
+    assert net.file_lists() == [["spk/0.wav", "spk/3.wav"], ["spk/1.wav", "spk/2.wav"]]      # lib.rs:723
+    assert float(oracle.lr_decay(0.05, 7)) < 0.05 * 0.99 ** 6                                # the step counter really decays
+
+
+def test_back_to_back_dev_batches_keep_their_own_segment_tables(sz, ctx, oracle, native):
+    # The *_dev entry points return without synchronising; each call's segment table / offset table must survive until its
+    # own H2D copy has run (a single pinned staging buffer used to be overwritten by the next call).
+    import ctypes as C
+    clips_a = [oracle.synth_clip(0, 41, 0.3), oracle.synth_clip(1, 42, 0.5)]
+    clips_b = [oracle.synth_clip(2, 43, 0.45), oracle.synth_clip(3, 44, 0.2), oracle.synth_clip(4, 45, 0.33)]
     ex = sz.FeatureExtractor(ctx)
-    net = sz.SimpleNeuralNet(60, 512, 256, 2, seed=3, ctx=ctx)
-    clip = oracle.synth_clip(0, 9, 1.0)
-    first = sz.pretrain_network(net, clip, 0, 2, 1, 0.01, 0.2, 8, ex, seed=1)
-    later = sz.pretrain_network(net, clip, 0, 2, 3, 0.01, 0.2, 8, ex, seed=2)
-    assert np.isfinite(first) and later < first
-    assert sz.pretrain_network(net, clip[:500], 0, 2, 2, 0.01, 0.2, 8, ex) == 0.0   # no windows -> 0 (lib.rs:392-396)
+    want_a, want_b = ex.extract_batch(clips_a), ex.extract_batch(clips_b)
+    outs = []
+    bufs = []
+    for rep in range(6):                                           # A, B, A, B ... queued with no sync in between
+        clips = clips_a if rep % 2 == 0 else clips_b
+        pcm, off = sz.pack_clips(clips)
+        d_pcm = ctx.dev_alloc(pcm.nbytes + 64)
+        ctx.h2d(d_pcm, pcm)
+        total = int(native.lib.szb_extract_batch_windows(native.ptr(off), len(clips), 44100))
+        d_out = ctx.dev_alloc(total * 240)
+        bufs.append((d_pcm, d_out, total, off))
+    for d_pcm, d_out, total, off in bufs:
+        woff = np.zeros(len(off), np.uint64)
+        native.check(native.lib.szb_extract_batch_dev(ctx.handle, C.c_void_p(d_pcm), native.ptr(off), len(off) - 1, 44100,
+                                                      C.c_void_p(d_out), total, native.ptr(woff)))
+    ctx.sync()
+    for rep, (d_pcm, d_out, total, off) in enumerate(bufs):
+        got = np.empty((total, 60), np.float32)
+        ctx.d2h(got, d_out)
+        want = np.concatenate(want_a if rep % 2 == 0 else want_b)
+        assert np.array_equal(got, want), rep
+        ctx.dev_free(d_pcm); ctx.dev_free(d_out)

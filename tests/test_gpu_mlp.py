@@ -214,3 +214,83 @@ def test_cached_features(sz, ctx, oracle, tmp_path, monkeypatch):
     assert np.array_equal(np.load(tmp_path / "feature_cache" / "d_s.wav.npy"), a)     # lib.rs:550-579
     assert len(sz.load_cached_features("short.wav", lambda p: clip[:100], ex)) == 0
     assert not (tmp_path / "feature_cache" / "short.wav.npy").exists()                # empty sets are not written (lib.rs:573)
+
+
+def test_model_npz_keeps_embeddings_and_encoding_layer(sz, ctx, oracle, tmp_path):
+    # lib.rs:1099-1127 (save) / 1168-1264 (load): speaker_embeddings, speaker_mean_sims, speaker_std_sims, w4_k / b4_k.
+    # The CLI sets the embeddings right before saving (main.rs:845-856); load -> save must lose nothing.
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 3), seed=4)
+    r = np.random.default_rng(3)
+    embeds = [(r.standard_normal(256).astype(np.float32), float(r.random()), float(r.random())) for _ in range(3)]
+    net.set_embeddings(embeds)
+    w4, b4 = r.standard_normal((40, 6)).astype(np.float32), r.standard_normal(6).astype(np.float32)   # its own row count (lib.rs:1211-1214)
+    net.set_encoding_layer(w4, b4)
+    path = str(tmp_path / "model.npz")
+    net.save(path)
+    z = np.load(path)
+    assert z["speaker_embeddings"].shape == (3, 256) and z["speaker_embeddings"].dtype == np.float32
+    assert np.array_equal(z["speaker_embeddings"], np.stack([e[0] for e in embeds]))
+    assert np.array_equal(z["speaker_mean_sims"], np.array([e[1] for e in embeds], np.float32))
+    assert np.array_equal(z["speaker_std_sims"], np.array([e[2] for e in embeds], np.float32))
+    for k in range(6):
+        assert np.array_equal(z[f"w4_{k + 1}"], w4[:, k]) and z[f"b4_{k + 1}"][0] == b4[k]
+    # member order of the reference writer (lib.rs:1084-1127)
+    order = list(z.files)
+    assert order.index("b3_3") < order.index("w4_1") < order.index("speaker_0_files") < order.index("speaker_embeddings")
+    back = sz.SimpleNeuralNet.load(path, ctx=ctx)
+    got = back.embeddings()
+    assert len(got) == 3 and all(np.array_equal(a[0], b[0]) and a[1] == np.float32(b[1]) and a[2] == np.float32(b[2])
+                                 for a, b in zip(got, embeds))
+    gw4, gb4 = back.encoding_layer()
+    assert np.array_equal(gw4, w4) and np.array_equal(gb4, b4)
+    p2 = str(tmp_path / "again.npz")
+    back.save(p2)
+    assert open(path, "rb").read() == open(p2, "rb").read()          # load -> save is the identity on the file
+    fresh = sz.SimpleNeuralNet(60, 8, 4, 2, ctx=ctx)
+    assert fresh.embeddings() == [] and fresh.encoding_layer() is None
+    p3 = str(tmp_path / "plain.npz")
+    fresh.save(p3)
+    assert "speaker_embeddings" not in np.load(p3).files and "w4_1" not in np.load(p3).files   # only when non-empty (lib.rs:1114)
+
+
+def test_npz_and_npy_readers_reject_malformed_files(sz, ctx, native, tmp_path):
+    # every one of these used to over-read, wrap an index or throw through the C ABI
+    import ctypes as C
+    import struct
+    good = str(tmp_path / "m.npz")
+    sz.SimpleNeuralNet(60, 8, 4, 2, ctx=ctx).save(good)
+    raw = bytearray(open(good, "rb").read())
+
+    def load_status(data):
+        p = str(tmp_path / "bad.npz")
+        open(p, "wb").write(bytes(data))
+        h, sr, bits = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        st = native.lib.szb_net_load(ctx.handle, p.encode(), C.byref(h), C.byref(sr), C.byref(bits))
+        if st == 0:
+            native.lib.szb_net_destroy(h)
+        return st
+
+    assert load_status(raw) == 0
+    eocd = raw.rfind(b"PK\x05\x06")
+    cd = struct.unpack_from("<I", raw, eocd + 16)[0]
+    bad = bytearray(raw); struct.pack_into("<H", bad, cd + 28, 0xFFFF)          # name length past the end of the file
+    assert load_status(bad) == native.ERR_IO
+    bad = bytearray(raw); struct.pack_into("<I", bad, cd + 42, 0xFFFFFFF0)      # local header offset that wraps in 32 bits
+    assert load_status(bad) == native.ERR_IO
+    bad = bytearray(raw); struct.pack_into("<I", bad, cd + 20, 0xFFFFFF00); struct.pack_into("<I", bad, cd + 24, 0xFFFFFF00)
+    assert load_status(bad) == native.ERR_IO                                      # member size past the end
+    assert load_status(raw[:40]) == native.ERR_IO
+
+    def npy_status(header):
+        p = str(tmp_path / "bad.npy")
+        h = header.encode()
+        open(p, "wb").write(b"\x93NUMPY\x01\x00" + struct.pack("<H", len(h)) + h + b"\x00" * 64)
+        rows, cols = C.c_uint64(), C.c_uint64()
+        buf = np.zeros(16, np.float32)
+        return native.lib.szb_npy_read_f32(p.encode(), native.ptr(buf), 16, C.byref(rows), C.byref(cols))
+
+    assert npy_status("{'descr': '<f4', 'fortran_order': False, 'shape': (2, 8), }\n") == 0
+    assert npy_status("{'descr': '<f4', 'fortran_order': False, 'shape': (4611686018427387904, 4), }\n") == native.ERR_IO   # count * 4 wraps
+    assert npy_status("{'descr' '<f4', 'fortran_order' False, 'shape' (2, 8), }\n") == native.ERR_IO                      # no ':' at all
+    assert npy_status("{'descr': '<f4', 'fortran_order':") == native.ERR_IO
+    assert npy_status("{'descr': '<f4', 'fortran_order': False, 'shape': (2, 8") == native.ERR_IO
