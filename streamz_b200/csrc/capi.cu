@@ -187,7 +187,7 @@ void szb_ctx_destroy(szb_ctx* ctx) {
     }
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
-                       &ctx->x, &ctx->loop_pcm, &ctx->loop_labels })
+                       &ctx->x, &ctx->loop_pcm, &ctx->loop_labels, &ctx->p2p_counters })
         b->release();
     ctx->h_stage.release();
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);

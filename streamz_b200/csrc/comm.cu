@@ -95,15 +95,18 @@ szb_status comm_join(szb_ctx* ctx) {
 }
 
 // ---- gradient exchange over peer memory ------------------------------------------------------------------------------
-// Region layout per rank: [flags: kMaxPeers x u32, padded to 256 B][grad buffer 0: cap floats][grad buffer 1: cap floats].
+// Region layout per rank: [flag block, 256 B: u32 words 0-15 flag1 per source rank, 16-31 flag2, 48 spare (teardown
+// rendezvous)][inbox: cap floats][red: cap floats]  (protocol: mlp.cu, p2p_exchange).
 constexpr size_t kP2pCapFloats = size_t(1) << 20;   // 4 MB per buffer: nets up to ~1 M parameters (C = 1000: 420 k)
 constexpr size_t kP2pFlagBytes = 256;
+constexpr size_t kP2pSpareWord = 48;
 
 static void p2p_teardown(szb_ctx* ctx) {
     for (int r = 0; r < ctx->world && r < szb_ctx::kMaxPeers; ++r) {
         if (r != ctx->rank && ctx->p2p_flags[r]) cudaIpcCloseMemHandle(ctx->p2p_flags[r]);
         ctx->p2p_flags[r] = nullptr;
-        ctx->p2p_grad[r] = nullptr;
+        ctx->p2p_inbox[r] = nullptr;
+        ctx->p2p_red[r] = nullptr;
     }
     if (ctx->p2p_region) cudaFree(ctx->p2p_region);
     ctx->p2p_region = nullptr;
@@ -141,7 +144,8 @@ static szb_status p2p_setup(szb_ctx* ctx) {
             void* base = ctx->p2p_region;
             if (r != me && cudaIpcOpenMemHandle(&base, all[size_t(r)].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
             ctx->p2p_flags[r] = static_cast<uint32_t*>(base);
-            ctx->p2p_grad[r] = reinterpret_cast<float*>(static_cast<char*>(base) + kP2pFlagBytes);
+            ctx->p2p_inbox[r] = reinterpret_cast<float*>(static_cast<char*>(base) + kP2pFlagBytes);
+            ctx->p2p_red[r] = ctx->p2p_inbox[r] + kP2pCapFloats;
         }
         cudaGetLastError();
     }
@@ -158,6 +162,8 @@ static szb_status p2p_setup(szb_ctx* ctx) {
         p2p_teardown(ctx);
         return SZB_OK;
     }
+    SZB_TRY(ctx->p2p_counters.reserve(2 * sizeof(unsigned int)));
+    SZB_CUDA(cudaMemset(ctx->p2p_counters.ptr, 0, 2 * sizeof(unsigned int)));
     ctx->p2p_on = true;
     ctx->p2p_cap = kP2pCapFloats;
     ctx->p2p_step = 0;
@@ -199,7 +205,7 @@ szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active)
         if (enable && !ctx->p2p_on) SZB_TRY(p2p_setup(ctx));
         if (!enable && ctx->p2p_on) {
             cudaStreamSynchronize(ctx->stream);
-            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + szb_ctx::kMaxPeers;
+            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + kP2pSpareWord;
             SZB_NCCL(g_nccl.AllReduce(d, d, 1, 7, 0, ctx->nccl_comm, ctx->stream));   // peers may still be reading
             SZB_CUDA(cudaStreamSynchronize(ctx->stream));
             p2p_teardown(ctx);
@@ -216,7 +222,7 @@ szb_status szb_comm_destroy(szb_ctx* ctx) {
         if (ctx->p2p_on) {
             // peers may still be reading this rank's gradients: rendezvous before the region goes away
             cudaStreamSynchronize(ctx->stream);
-            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + szb_ctx::kMaxPeers;   // spare words of the flag block
+            float* d = reinterpret_cast<float*>(ctx->p2p_flags[ctx->rank]) + kP2pSpareWord;        // spare word of the flag block
             g_nccl.AllReduce(d, d, 1, 7, 0, ctx->nccl_comm, ctx->stream);
             cudaStreamSynchronize(ctx->stream);
         }

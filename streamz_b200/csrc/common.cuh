@@ -103,16 +103,20 @@ struct szb_ctx {
     cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the rest of the backward pass
     cudaEvent_t ev_comm = nullptr;
     int rank = 0, world = 1;
-    // Gradient exchange over NVLink peer memory (comm.cu): every rank's [2][p2p_cap] gradient buffers and flag words are
-    // mapped into every other rank with CUDA IPC, and sgd_p2p_kernel (mlp.cu) reduces the peers' gradients and applies the
-    // update in ONE kernel -- no NCCL call inside a training step.  Off (NCCL all-reduce) when IPC / peer access is missing.
+    // Gradient exchange over NVLink peer memory (comm.cu): every rank's exchange region [flags | inbox | red] is mapped
+    // into every other rank with CUDA IPC, and the update kernels (mlp.cu: p2p_exchange) run a two-shot all-reduce made of
+    // peer stores in the same launch as the SGD update -- no NCCL call inside a training step.  Off (NCCL all-reduce) when
+    // IPC / peer access is missing.
     static constexpr int kMaxPeers = 16;
     bool p2p_on = false;
-    size_t p2p_cap = 0;                       // floats per gradient buffer
+    size_t p2p_cap = 0;                       // floats per buffer (inbox, red)
     uint32_t p2p_step = 0;                    // steps exchanged so far (flag value of the next step = p2p_step + 1)
-    float* p2p_grad[kMaxPeers] = {};          // gradient double buffer of every rank ([rank] is local memory)
-    uint32_t* p2p_flags[kMaxPeers] = {};      // flag words of every rank: p2p_flags[r][s] = last step rank s has published to r
-    void* p2p_region = nullptr;               // local allocation backing p2p_grad[rank] and p2p_flags[rank]
+    float* p2p_inbox[kMaxPeers] = {};         // [world][slice] partial slices received from every rank ([rank] is local memory)
+    float* p2p_red[kMaxPeers] = {};           // the reduced gradient vector as every rank receives it
+    uint32_t* p2p_flags[kMaxPeers] = {};      // flag block of every rank: [s] / [16 + s] = last step rank s finished phase 0 / 1 for
+    szb::DevBuf p2p_counters;                 // private last-CTA tickets of the two phases
+    int p2p_max_blocks = 0;                   // co-resident CTA capacity of the update kernels (0 = not queried yet)
+    void* p2p_region = nullptr;               // local allocation backing p2p_flags / p2p_inbox / p2p_red of this rank
 };
 
 namespace szb {

@@ -349,18 +349,110 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
         params[i] -= grads[i] * scale;
 }
 
+// ---- multi-GPU gradient exchange over NVLink peer memory, fused into the update kernels ---------------------------------
+// Every rank's exchange region (comm.cu: [flags | inbox | red]) is mapped into all ranks with CUDA IPC.  A step's gradient
+// vector V = G[0, nv) (nv = parameters + the two [n_used, loss, ..] tail blocks) is cut into `world` contiguous slices of
+// slice_g 16-byte groups; rank r OWNS slice r.  The exchange is a two-shot all-reduce made of posted peer STORES only --
+// no rank ever waits on a remote load -- in the same launch as the SGD update:
+//   phase 0  scatter : every rank stores slice d of its private gradient into inbox[me] of rank d   (1/world of V per peer)
+//            ...  the last CTA to finish publishes flag1[me] = step on every peer (release, system scope)
+//   phase 1  reduce  : wait flag1 from all ranks (acquire); the owner sums its `world` inbox rows IN RANK ORDER (its own
+//            row straight from G) and stores the reduced slice into `red` of EVERY rank;  last CTA publishes flag2[me]
+//   phase 2  update  : wait flag2 from all ranks; red (local memory) now holds the whole reduced vector: the ordinary
+//            update runs on it.  Each element is summed by exactly one rank in a fixed order and broadcast, so the replicas
+//            stay bit-identical (tested) and equal the old one-shot pull bit for bit.
+// Round 1's one-shot pull read all `world` full vectors per rank with dependent 4-byte peer loads (0.39 per-GPU efficiency at
+// 8 GPUs, 259 us per step) and needed a 753 KB device-to-device copy per step; here a rank moves 2 (world-1)/world of V in
+// posted stores and the copy is gone (phase 0 reads G directly).
+// Buffer reuse needs no double buffering: a rank enters step t+1 only after it has seen flag2(t) from every rank, and a rank
+// publishes flag2(t) only after it has finished reading its inbox(t); `red` of rank d is rewritten in phase 1 of step t+1,
+// which the writers enter only after flag1(t+1) from d, i.e. after d's step-t kernel (the reader of red) has completed.
 struct P2pArgs {
-    const float* grad[szb_ctx::kMaxPeers];   // this step's gradient vector of every rank
-    uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank
+    float* inbox[szb_ctx::kMaxPeers];        // inbox of every rank: [world][slice_g * 4] floats, row = source rank
+    float* red[szb_ctx::kMaxPeers];          // reduced-vector buffer of every rank
+    uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank: [0, 16) flag1 per source rank, [16, 32) flag2
+    unsigned int* counters;                  // private: [0] CTAs done with phase 0, [1] with phase 1 (last-CTA detection)
     int rank, world;
     uint32_t step;
+    uint32_t n4, slice_g;                    // 16-byte groups in V, groups per slice
 };
 
-// Peer data is read with ordinary L1-bypassing loads (ld.global.cg): they are ordered after the acquire of the flags by
-// the block barrier, the owner's L2 serves them, and -- unlike volatile / strong system-scope loads, measured at ~12 us
-// per peer -- the hardware keeps all of them in flight at once.
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float ld_peer_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ void p2p_wait_flags(const uint32_t* f, int world, uint32_t step) {
+    if (int(threadIdx.x) < world) {
+        const uint32_t* p = f + threadIdx.x;
+        uint32_t seen = 0;
+        unsigned long long t0 = 0;
+        for (uint32_t spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p) : "memory");
+            if (int32_t(seen - step) >= 0) break;
+            __nanosleep(32);
+            if ((spin & 0xFFFFu) == 0xFFFFu) {             // a peer that is minutes late has died: never hang the GPU
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 180ull * 1000000000ull) __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Called by every thread of every CTA when this CTA's stores of a phase are issued: the LAST CTA of the grid to arrive
+// publishes `step` into flag word (base + rank) of every peer.  (stores -> bar -> fence.sys -> ticket) is the release
+// pattern, (ticket -> fence.sys -> flag store.release) chains it to the peers' acquire loads.
+__device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* counter, int flag_base) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        s_last = ticket == gridDim.x - 1;
+        if (s_last) *counter = 0u;                         // every CTA has arrived; the next step finds it zero
+    }
+    __syncthreads();
+    if (s_last && int(threadIdx.x) < a.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + flag_base + a.rank), "r"(a.step) : "memory");
+    }
+}
+
+// Phases 0 and 1.  On return (all threads of the CTA) the local `red` buffer holds the rank-ordered sum of every rank's
+// V; read it with L1-bypassing loads (peers wrote it).
+__device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const float* __restrict__ G) {
+    const int me = a.rank, W = a.world;
+    const size_t nthreads = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const float4* G4 = reinterpret_cast<const float4*>(G);
+    // ---- phase 0: scatter my slices to their owners (my own slice stays in G)
+    for (size_t i = t0; i < a.n4; i += nthreads) {
+        const uint32_t d = uint32_t(i / a.slice_g);
+        if (int(d) == me) continue;
+        const float4 v = G4[i];
+        reinterpret_cast<float4*>(a.inbox[d])[size_t(me) * a.slice_g + (i - size_t(d) * a.slice_g)] = v;
+    }
+    p2p_publish(a, a.counters + 0, 0);
+    // ---- phase 1: reduce my slice in rank order, broadcast it
+    p2p_wait_flags(a.flags[me], W, a.step);
+    const size_t g0 = size_t(me) * a.slice_g;
+    const size_t mine = g0 < a.n4 ? min(size_t(a.slice_g), size_t(a.n4) - g0) : 0;
+    const float4* in4 = reinterpret_cast<const float4*>(a.inbox[me]);
+    for (size_t o = t0; o < mine; o += nthreads) {
+        float4 v[szb_ctx::kMaxPeers];                       // all rows requested before the first add
+#pragma unroll
+        for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+            if (r < W) v[r] = r == me ? G4[g0 + o] : __ldcg(in4 + size_t(r) * a.slice_g + o);
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < szb_ctx::kMaxPeers; ++r)
+            if (r < W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+            if (r < W) reinterpret_cast<float4*>(a.red[r])[g0 + o] = s;
+    }
+    p2p_publish(a, a.counters + 1, 16);
+    // ---- phase 2 entry: everybody's reduced slice has landed here
+    p2p_wait_flags(a.flags[me] + 16, W, a.step);
+    return a.red[me];
+}
 
 // Tensor-core path: the SGD update, the refresh of the transposed weight copies the GEMMs read, and the zeroing of the
 // gradient vector for the next step in ONE pass (three launches -- sgd, transpose, 753 KB memset -- become one).
@@ -368,6 +460,8 @@ __device__ __forceinline__ float ld_peer_f(const float* p) { return __ldcg(p); }
 // (lanes along n), the updated tile crosses a padded shared-memory tile and leaves for WT[n][k] as 128-byte segments along
 // k.  The blocks past the last tile update the biases.  (The first version walked WT linearly with two integer divisions
 // per element and lane-strided reads of P and G: 8 us per step against ~3 us now.)
+// Multi-GPU (a.world > 1): the kernel starts with the two-shot gradient exchange above; every CTA of the grid must be
+// resident at once (the launch keeps the grid below the device's capacity for this kernel).
 __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ WT, int n_in,
                                                         int h1, int h2, int n_out, size_t off_b1, size_t off_w2, size_t off_b2,
                                                         size_t off_w3, size_t off_b3, size_t off_wt2, size_t off_wt3, size_t np, int parity,
@@ -375,45 +469,18 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     __shared__ float tile[32][33];
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    // a.world > 1: the gradient of the step is the sum over the ranks' exchange buffers (peer memory, see sgd_p2p_kernel
-    // below for the flag protocol); G is this rank's private accumulation buffer, which is only zeroed here.
     const bool peers = a.world > 1;
-    if (peers) {
-        if (blockIdx.x == 0 && threadIdx.x < a.world) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + a.rank), "r"(a.step) : "memory");
-        }
-        if (threadIdx.x < a.world) {
-            const uint32_t* f = a.flags[a.rank] + threadIdx.x;
-            uint32_t seen = 0;
-            unsigned long long t0 = 0;
-            for (uint32_t spin = 0;; ++spin) {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-                if (int32_t(seen - a.step) >= 0) break;
-                __nanosleep(64);
-                if ((spin & 0xFFFFu) == 0xFFFFu) {             // a peer that is minutes late has died: never hang the GPU
-                    unsigned long long t;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                    if (t0 == 0) t0 = t;
-                    else if (t - t0 > 180ull * 1000000000ull) __trap();
-                }
-            }
-        }
-        __syncthreads();
-    }
-    auto grad_at = [&](size_t idx) -> float {        // summed in rank order: identical bits on every rank
-        if (!peers) return G[idx];
-        float g = 0.f;
-        for (int r = 0; r < a.world; ++r) g += ld_peer_f(a.grad[r] + idx);
-        return g;
-    };
+    const float* R = peers ? p2p_exchange(a, G) : G;     // the step's (reduced) gradient vector
+    auto grad_at = [&](size_t idx) -> float { return peers ? __ldcg(R + idx) : R[idx]; };
     const float n_used = grad_at(np + 4 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (stats) {
             stats[0] += double(grad_at(np + 4 * parity + 1));  // loss
             stats[1] += double(n_used);
         }
-        G[np + 4 * (1 - parity)] = 0.f;                  // the next step's block (nobody reads it during this launch)
+        // the next step's tail block: nobody reads it during this launch (in a multi-GPU step every CTA of this rank has
+        // finished reading G in phase 0 before any CTA gets here)
+        G[np + 4 * (1 - parity)] = 0.f;
         G[np + 4 * (1 - parity) + 1] = 0.f;
     }
     const float scale = n_used > 0.f ? lr / n_used : 0.f;   // empty batch: gradients are zero, nothing moves (lib.rs:1003-1005)
@@ -458,68 +525,19 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     }
 }
 
-// Multi-GPU step: gradient all-reduce and SGD update in ONE kernel over NVLink peer memory (no NCCL call in the step).
-// Every rank's gradient vector [g | n_used, loss, ..] of this step sits in its own memory, mapped into all ranks (CUDA IPC,
-// comm.cu).  (1) publish: this rank's backward pass is complete (stream order), so one thread stores the step number into
-// its flag slot on every peer (release, system scope).  (2) wait: each block polls the local flag block until every peer has
-// published this step (acquire).  (3) reduce + update: each thread loads its slice of all `world` gradient vectors straight
-// from the peers (volatile 128-bit loads: served by the owner's L2, never a stale local line), adds them in rank order --
-// the same order on every rank, so the replicas stay bit-identical -- and applies theta -= (lr / sum n_used) * sum g.
-// The buffers alternate by step parity: a rank can only overwrite buffer b two steps later, after every peer has
-// published the step in between, i.e. has finished reading b.
-__global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params, const __grid_constant__ P2pArgs a, size_t n, float lr,
-                                                      double* __restrict__ stats) {
-    if (blockIdx.x == 0 && threadIdx.x < a.world) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + a.rank), "r"(a.step) : "memory");
-    }
-    if (threadIdx.x < a.world) {
-        const uint32_t* f = a.flags[a.rank] + threadIdx.x;
-        uint32_t seen = 0;
-        unsigned long long t0 = 0;
-        for (uint32_t spin = 0;; ++spin) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-            if (int32_t(seen - a.step) >= 0) break;
-            __nanosleep(64);
-            if ((spin & 0xFFFFu) == 0xFFFFu) {             // a peer that is minutes late has died: never hang the GPU
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t0 == 0) t0 = t;
-                else if (t - t0 > 180ull * 1000000000ull) __trap();
-            }
-        }
-    }
-    __syncthreads();
-    float n_used = 0.f, loss = 0.f;
-    for (int r = 0; r < a.world; ++r) {
-        n_used += ld_peer_f(a.grad[r] + n);
-        loss += ld_peer_f(a.grad[r] + n + 1);
-    }
+// FP32 (CUDA-core) path of a multi-GPU step: the same exchange, then the plain update theta -= (lr / sum n_used) * sum g.
+__global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params, const float* __restrict__ G,
+                                                      const __grid_constant__ P2pArgs a, size_t n, float lr, double* __restrict__ stats) {
+    const float* R = p2p_exchange(a, G);
+    const float n_used = __ldcg(R + n), loss = __ldcg(R + n + 1);
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
         stats[0] += double(loss);
         stats[1] += double(n_used);
     }
     if (n_used <= 0.f) return;             // empty global batch: no-op (lib.rs:1003-1005)
     const float scale = lr / n_used;
-    const size_t n4 = n / 4;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
-        float4 v[szb_ctx::kMaxPeers];                      // all peers' loads in flight together, summed in rank order
-#pragma unroll
-        for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
-            if (r < a.world) v[r] = ld_peer_f4(a.grad[r] + 4 * i);
-        float4 g = v[0];
-#pragma unroll
-        for (int r = 1; r < szb_ctx::kMaxPeers; ++r)
-            if (r < a.world) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }
-        float4 p = reinterpret_cast<float4*>(params)[i];
-        p.x -= g.x * scale; p.y -= g.y * scale; p.z -= g.z * scale; p.w -= g.w * scale;
-        reinterpret_cast<float4*>(params)[i] = p;
-    }
-    for (size_t i = 4 * n4 + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-        float g = 0.f;
-        for (int r = 0; r < a.world; ++r) g += ld_peer_f(a.grad[r] + i);
-        params[i] -= g * scale;
-    }
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        params[i] -= __ldcg(R + i) * scale;
 }
 
 __global__ void init_uniform_kernel(float* __restrict__ w, size_t n, unsigned long long key, unsigned long long base) {
@@ -743,10 +761,10 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
     const size_t np = net->n_params();
-    // multi-GPU with peer-mapped exchange buffers (comm.cu).  The gradient is still accumulated in private memory and
-    // copied into this step's exchange buffer afterwards: the split-K atomics of the weight-gradient GEMMs run 2.2x slower
-    // on IPC-exported memory (measured: 105 vs 48 ms per epoch at N = 2 when they accumulate there directly).
-    const bool p2p = ctx->world > 1 && ctx->p2p_on && np + kGradTail <= ctx->p2p_cap;
+    // multi-GPU with peer-mapped exchange buffers (comm.cu).  The gradient is accumulated in private memory (the split-K
+    // atomics of the weight-gradient GEMMs run 2.2x slower on IPC-exported memory: 105 vs 48 ms per epoch at N = 2) and the
+    // update kernel scatters it to the slice owners itself -- no staging copy.
+    const bool p2p = ctx->world > 1 && ctx->p2p_on && np + kGradTail + 4 * size_t(ctx->world) + 4 <= ctx->p2p_cap;
     float* G = net->grads.as<float>();
     // single-context tensor-core steps end in sgd_fused_kernel, which leaves the gradient vector zeroed for the next step
     const bool fused = net->precision != 0;   // (with the peer exchange the same kernel also sums the ranks' gradients)
@@ -844,26 +862,39 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     }
     P2pArgs a{};
     a.world = 1;
+    int p2p_blocks = 0;
     if (p2p) {
-        SZB_CUDA(cudaMemcpyAsync(ctx->p2p_grad[ctx->rank] + size_t(ctx->p2p_step & 1u) * ctx->p2p_cap, G, (np + kGradTail) * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        const size_t nv = np + kGradTail;
+        a.n4 = uint32_t((nv + 3) / 4);
+        a.slice_g = (a.n4 + uint32_t(ctx->world) - 1) / uint32_t(ctx->world);
         for (int r = 0; r < ctx->world; ++r) {
-            a.grad[r] = ctx->p2p_grad[r] + size_t(ctx->p2p_step & 1u) * ctx->p2p_cap;
+            a.inbox[r] = ctx->p2p_inbox[r];
+            a.red[r] = ctx->p2p_red[r];
             a.flags[r] = ctx->p2p_flags[r];
         }
+        a.counters = ctx->p2p_counters.as<unsigned int>();
         a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
+        // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
+        if (ctx->p2p_max_blocks == 0) {
+            int per_sm_fused = 0, per_sm_plain = 0;
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 0));
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_plain, sgd_p2p_kernel, 256, 0));
+            ctx->p2p_max_blocks = std::max(1, std::min(per_sm_fused, per_sm_plain)) * ctx->sm_count;
+        }
+        p2p_blocks = ctx->p2p_max_blocks;
     }
     if (fused) {
         SZB_TRY(net->wt.reserve(net->n_wt() * 4));
         const int tiles = int(((net->n_in + 31) / 32) * ((net->h1 + 31) / 32) + ((net->h1 + 31) / 32) * ((net->h2 + 31) / 32) +
                               ((net->h2 + 31) / 32) * ((net->n_out + 31) / 32));
-        const int blocks = std::max(1, std::min(tiles + 1, ctx->sm_count * 4));
+        int blocks = std::max(1, std::min(tiles + 1, ctx->sm_count * 4));
+        if (p2p) blocks = std::min(blocks, p2p_blocks);
         SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
                             int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
                             net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a));
     } else if (p2p) {
-        const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(ctx->sm_count)));
-        sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, a, np, lr, net->stats.as<double>());
+        const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(std::min(ctx->sm_count * 2, p2p_blocks))));
+        sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, G, a, np, lr, net->stats.as<double>());
     } else {
         const int blocks = int(std::min<size_t>((np + 255) / 256, size_t(ctx->sm_count) * 4));
         sgd_kernel<<<blocks, 256, 0, ctx->stream>>>(P, G, np, lr, net->stats.as<double>());

@@ -1,5 +1,7 @@
-"""Two ranks on two GPUs (one process per GPU, NCCL): batch-parallel training must reproduce the single-GPU epoch, and
-clip-sharded extraction must reproduce the single-GPU features.  Skipped when fewer than 2 GPUs are visible."""
+"""2 / 4 / 8 ranks on as many GPUs (one process per GPU): batch-parallel training must reproduce the single-GPU epoch with
+either gradient exchange (NCCL all-reduces, or the two-shot peer-memory exchange fused into the update kernel) and leave
+bit-identical replicas; clip-sharded extraction must reproduce the single-GPU features.  A world size is skipped when
+fewer GPUs are visible (the driver's 1-GPU box skips all three; `gpurun --gpus 8` runs all three, log under profiles/)."""
 import os
 import socket
 import sys
@@ -37,25 +39,33 @@ def _worker(rank, world, port, tmp):
         local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
         loss, used = sz.train_epoch_steps(net, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
         tot += loss; cnt += used
-    # the same two epochs again with the fused peer-memory exchange (one kernel: flags + peer loads + SGD) instead of NCCL
+    # the same two epochs again with the two-shot peer-memory exchange fused into the update kernel instead of NCCL,
+    # on the tensor-core path (sgd_fused_kernel) and on the FP32 CUDA-core path (sgd_p2p_kernel)
     peer = ctx.comm_peer_exchange(True)
-    net2 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx)
-    for epoch in range(2):
-        local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
-        sz.train_epoch_steps(net2, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
-    w2 = net2.weights()
+    w2, w3 = None, None
+    for mode in ("3xtf32", "fp32"):
+        net2 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx).set_precision(mode)
+        for epoch in range(2):
+            local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
+            sz.train_epoch_steps(net2, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
+        if mode == "3xtf32":
+            w2 = net2.weights()
+        else:
+            w3 = net2.weights()
     ctx.comm_peer_exchange(False)
     # extraction: each rank takes its clip range, no collective
     clips = [d[f"clip{i}"] for i in range(6)]
     lo, hi = shard_clips([len(c) for c in clips], world)[rank]
     feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
-    np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+    np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)},
+             **{f"r{i}": w for i, w in enumerate(w3)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
     dist.destroy_process_group()
 
 
-def test_two_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_path):
-    if _gpu_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_path, world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     r = np.random.default_rng(9)
     n = 1000
@@ -67,7 +77,7 @@ def test_two_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_p
     np.savez(str(tmp_path / "data.npz"), feats=feats, labels=labels, perm0=perms[0], perm1=perms[1],
              **{f"p{i}": p for i, p in enumerate(onet.params())}, **{f"clip{i}": c for i, c in enumerate(clips)})
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     # single-GPU run of the same epochs
     net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
     data = sz.DeviceFeatures(ctx, feats, labels)
@@ -75,18 +85,25 @@ def test_two_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp_p
     for epoch in range(2):
         loss, used = sz.train_epoch(net, data, perms[epoch], 96, 0.02, dropout=0.2, seed=77, stream=epoch)
         tot += loss; cnt += used
-    outs = [np.load(str(tmp_path / f"out{k}.npz")) for k in range(2)]
-    for k in range(2):
+    net32 = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx).set_precision("fp32")
+    for epoch in range(2):
+        sz.train_epoch(net32, data, perms[epoch], 96, 0.02, dropout=0.2, seed=77, stream=epoch)
+    outs = [np.load(str(tmp_path / f"out{k}.npz")) for k in range(world)]
+    for k in range(world):
         assert int(outs[k]["used"]) == cnt and abs(float(outs[k]["loss"]) - tot) <= 1e-3 * abs(tot)
         for i, w in enumerate(net.weights()):
             assert np.abs(outs[k][f"arr_{i}"] - w).max() <= 1e-5          # both replicas == the single-GPU result
             assert bool(outs[k]["peer"])                                  # B200 boxes have NVLink peer access
             assert np.abs(outs[k][f"q{i}"] - w).max() <= 1e-5             # ... with either gradient exchange
-    for i in range(6):
-        assert np.array_equal(outs[0][f"q{i}"], outs[1][f"q{i}"])         # rank-ordered sums: bit-identical replicas
+        for i, w in enumerate(net32.weights()):
+            assert np.abs(outs[k][f"r{i}"] - w).max() <= 1e-5             # FP32 path: sgd_p2p_kernel
+    for k in range(1, world):
+        for i in range(6):                                                # every slice is summed once, in rank order, and
+            assert np.array_equal(outs[0][f"q{i}"], outs[k][f"q{i}"])     # broadcast: bit-identical replicas
+            assert np.array_equal(outs[0][f"r{i}"], outs[k][f"r{i}"])
     single = sz.FeatureExtractor(ctx).extract_batch(clips)
     seen = 0
-    for k in range(2):
+    for k in range(world):
         for i in range(int(outs[k]["lo"]), int(outs[k]["hi"])):
             assert np.array_equal(outs[k][f"f{i}"], single[i]); seen += 1
     assert seen == 6
