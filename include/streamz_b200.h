@@ -61,6 +61,13 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out);
 void szb_ctx_destroy(szb_ctx* ctx);
 szb_status szb_ctx_sync(szb_ctx* ctx);
 int32_t szb_ctx_sm_count(const szb_ctx* ctx);
+/* OPTIONAL mode of the device-resident szb_extract_batch_dev with rate != 44100: the batch is processed in chunks whose
+ * 44.1 kHz intermediate (chunk_mb MB) is written by the resampler into a two-slot ring that stays in the 126 MB L2 and is
+ * read back by the extraction kernel from there, so it never makes the round trip through HBM.  streams = 2 runs the
+ * resampler of chunk k + 1 on a second stream under the tail of extraction k.  chunk_mb = 0 (the DEFAULT): one chunk,
+ * intermediate in HBM.  Results are identical in every setting; every chunked setting measured slower than the default on
+ * B200, which is why it is off. */
+szb_status szb_ctx_set_l2_ring(szb_ctx* ctx, int32_t chunk_mb, int32_t streams);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 uint64_t szb_ctx_launch_count(const szb_ctx* ctx);
 /* Device-time of the work enqueued between start and stop on the context's stream (CUDA events). */

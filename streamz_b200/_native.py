@@ -43,6 +43,7 @@ SIGNATURES = {
     "szb_ctx_destroy": (None, [vp]),
     "szb_ctx_sync": (i32, [vp]),
     "szb_ctx_sm_count": (i32, [vp]),
+    "szb_ctx_set_l2_ring": (i32, [vp, i32, i32]),
     "szb_ctx_launch_count": (u64, [vp]),
     "szb_timer_start": (i32, [vp]),
     "szb_timer_stop": (i32, [vp, P(f32)]),

@@ -152,6 +152,8 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
     if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
+    if (const char* e = getenv("SZB_L2_CHUNK_MB")) ctx->l2_chunk_mb = std::max(0, atoi(e));
+    if (const char* e = getenv("SZB_L2_STREAMS")) ctx->l2_streams = atoi(e) > 1 ? 2 : 1;
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
         ctx->own_stream = false;
@@ -167,6 +169,7 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_start);
     cudaEventCreate(&ctx->ev_stop);
+    for (cudaEvent_t& e : ctx->ring_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     szb_status s = upload_frontend_tables();
     if (s != SZB_OK) {
         szb_ctx_destroy(ctx);
@@ -186,6 +189,7 @@ void szb_ctx_destroy(szb_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ring_ev) if (e) cudaEventDestroy(e);
     for (DevBuf* b : { &ctx->segs, &ctx->counter, &ctx->pcm, &ctx->feats, &ctx->taps, &ctx->labels, &ctx->misc, &ctx->probs,
                        &ctx->x, &ctx->loop_pcm, &ctx->loop_labels, &ctx->p2p_counters })
         b->release();
@@ -204,6 +208,13 @@ szb_status szb_ctx_sync(szb_ctx* ctx) {
     return SZB_OK;
 }
 int32_t szb_ctx_sm_count(const szb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+szb_status szb_ctx_set_l2_ring(szb_ctx* ctx, int32_t chunk_mb, int32_t streams) {
+    SZB_REQUIRE(ctx && chunk_mb >= 0 && (streams == 1 || streams == 2), "szb_ctx_set_l2_ring: chunk_mb >= 0, streams 1 or 2");
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->l2_chunk_mb = chunk_mb;
+    ctx->l2_streams = streams;
+    return SZB_OK;
+}
 uint64_t szb_ctx_launch_count(const szb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 szb_status szb_timer_start(szb_ctx* ctx) {
@@ -435,9 +446,25 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     const bool piped = h_pcm != nullptr;
     const uint64_t first = clip_off[0];
 
-    // chunking: one chunk for the device-resident call, ~48 MB of traffic per chunk for the host call
+    // chunking: ~48 MB of traffic per chunk for the host call (PCIe pipeline).  Device-resident call with a resampler in
+    // front: chunks whose 44.1 kHz intermediate is a few tens of MB, written by the resampler into a two-slot ring that never
+    // leaves the 126 MB L2 -- the extraction kernel of the chunk reads it back from L2 and the slot is overwritten two chunks
+    // later, still dirty in cache, so the 2 x 8.8 GB round trip through HBM of the unchunked pipeline disappears (ncu DRAM
+    // bytes: profiles/).  Device-resident call at 44.1 kHz: one chunk.
+    const uint64_t l2_chunk_bytes = uint64_t(ctx->l2_chunk_mb) << 20;
+    const bool ring = resample && !piped && l2_chunk_bytes > 0;
     std::vector<uint32_t> chunk_begin{ 0 };
-    if (piped) {
+    if (ring) {
+        uint64_t acc = 0;
+        for (uint32_t c = 0; c < n_clips; ++c) {
+            const uint64_t b = (off44[c + 1] - off44[c]) * 2;
+            if (acc > 0 && acc + b > l2_chunk_bytes) {
+                chunk_begin.push_back(c);
+                acc = 0;
+            }
+            acc += b;
+        }
+    } else if (piped) {
         const uint64_t target = 48ull << 20;
         uint64_t acc = 0;
         for (uint32_t c = 0; c < n_clips; ++c) {
@@ -454,15 +481,27 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     const int16_t* d_pcm44 = d_pcm;   // device layout: clip c starts at d_pcm[clip_off[c] - first] (rate 44.1k) ...
     uint64_t* d_in_off = nullptr;
     uint64_t* d_out_off = nullptr;
+    std::vector<uint64_t> off_ring;   // ring mode: clip c's 44.1 kHz samples start at misc[off_ring[c]] (slot = chunk & 1)
     if (resample) {                   // ... or at misc[off44[c]] after the resampler
-        SZB_TRY(ctx->misc.reserve(off44[n_clips] * 2 + 64));
+        if (ring) {
+            uint64_t slot = 0;
+            for (size_t k = 0; k + 1 < chunk_begin.size(); ++k) slot = std::max(slot, off44[chunk_begin[k + 1]] - off44[chunk_begin[k]]);
+            slot = (slot + 127) & ~uint64_t(127);
+            off_ring.resize(size_t(n_clips) + 1, 0);
+            for (size_t k = 0; k + 1 < chunk_begin.size(); ++k)
+                for (uint32_t c = chunk_begin[k]; c < chunk_begin[k + 1]; ++c)
+                    off_ring[c] = (k & 1) * slot + (off44[c] - off44[chunk_begin[k]]);
+            SZB_TRY(ctx->misc.reserve(2 * slot * 2 + 64));
+        } else {
+            SZB_TRY(ctx->misc.reserve(off44[n_clips] * 2 + 64));
+        }
         SZB_TRY(ctx->labels.reserve((size_t(n_clips) + 1) * 2 * sizeof(uint64_t)));
         void* hp = nullptr;
         SZB_TRY(ctx->h_stage.acquire((size_t(n_clips) + 1) * 2 * sizeof(uint64_t), &hp));
         uint64_t* h = static_cast<uint64_t*>(hp);
         for (uint32_t c = 0; c <= n_clips; ++c) {
             h[c] = clip_off[c] - first;
-            h[n_clips + 1 + c] = off44[c];
+            h[n_clips + 1 + c] = ring ? off_ring[c] : off44[c];
         }
         SZB_CUDA(cudaMemcpyAsync(ctx->labels.ptr, h, (size_t(n_clips) + 1) * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
@@ -474,7 +513,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     std::vector<Segment> segs;
     std::vector<size_t> seg_begin(n_chunks + 1, 0);
     std::vector<uint64_t> seg_off(size_t(n_clips) + 1);
-    for (uint32_t c = 0; c <= n_clips; ++c) seg_off[c] = resample ? off44[c] : clip_off[c] - first;
+    for (uint32_t c = 0; c <= n_clips; ++c) seg_off[c] = resample ? (ring ? off_ring[c] : off44[c]) : clip_off[c] - first;
     for (size_t k = 0; k < n_chunks; ++k) {
         seg_begin[k] = segs.size();
         build_segments(seg_off.data(), woff.data(), chunk_begin[k], chunk_begin[k + 1], ctx->sm_count, segs);
@@ -511,9 +550,28 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
         if (resample) {
             uint64_t max_out = 0;
             for (uint32_t c = c0; c < c1; ++c) max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
-            SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
+            if (ring && ctx->l2_streams > 1) {
+                // resampler of chunk k on the side stream: it may run under the tail of extract(k - 1); it must wait for
+                // extract(k - 2), the last reader of its ring slot, and for the tables uploaded on the main stream
+                cudaStream_t side = ctx->copy_in;
+                if (k == 0) {
+                    SZB_CUDA(cudaEventRecord(ctx->ring_ev[4], ctx->stream));
+                    SZB_CUDA(cudaStreamWaitEvent(side, ctx->ring_ev[4], 0));
+                }
+                if (k >= 2) SZB_CUDA(cudaStreamWaitEvent(side, ctx->ring_ev[2 + (k & 1)], 0));     // extract(k - 2) done
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = side;
+                const szb_status st = launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>());
+                ctx->stream = main_stream;
+                SZB_TRY(st);
+                SZB_CUDA(cudaEventRecord(ctx->ring_ev[k & 1], side));
+                SZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ring_ev[k & 1], 0));
+            } else {
+                SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
+            }
         }
         SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats, aligned16));
+        if (ring && ctx->l2_streams > 1) SZB_CUDA(cudaEventRecord(ctx->ring_ev[2 + (k & 1)], ctx->stream));
         if (piped) {
             SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
             SZB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_events[2 * k + 1], 0));

@@ -90,6 +90,13 @@ struct szb_ctx {
     uint64_t ktime_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime_pending;
     std::vector<cudaEvent_t> pipe_events;                // chunk pipeline of szb_extract_batch
+    // device-resident resample -> extract, OPTIONAL: the 44.1 kHz intermediate in a two-slot ring sized to stay in L2
+    // (capi.cu).  Off by default -- measured on B200 (profiles/r02_l2_ring_sweep.txt): every setting is slower than the
+    // single-chunk pipeline (21.7 ms per configs[1] step): 29.6 ms at 96 MB chunks, 37.8 ms at 32 MB; relaunching the
+    // persistent extraction kernel per chunk costs more than the HBM round trip it saves (neither kernel is HBM-bound).
+    int l2_chunk_mb = 0;                                 // SZB_L2_CHUNK_MB (0 = one chunk, intermediate through HBM)
+    int l2_streams = 2;                                  // SZB_L2_STREAMS: resampler of chunk k + 1 under the tail of extract k
+    cudaEvent_t ring_ev[5] = {};                         // [0,1] resample done, [2,3] extract done (per slot), [4] tables uploaded
     // scratch
     szb::DevBuf segs, counter, pcm, feats, taps, labels, misc, probs, x;
     szb::StagingRing h_stage;

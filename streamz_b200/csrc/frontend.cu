@@ -273,56 +273,73 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
             __syncthreads();
 
             // ---- 7. delta, delta-delta, z-score and store for the windows whose +-2 neighbours are now known.
-            //         warp = window, lane = coefficient j (< 20): the 60-value mean / variance is a warp shuffle
-            //         reduction, the three 20-float thirds of the row are stored straight to global memory (80
-            //         contiguous bytes per store) -- no further block barrier, no shared staging. ----------------------
+            //         LANE = WINDOW, warp = coefficient j (as in stage 6): a thread forms (c, d, dd) of its window for one j
+            //         from 5 ring words (consecutive lanes -> consecutive words), the 60-value moments cross the warps through
+            //         shared memory (two warps add the 20 partial sums), and the normalised rows make one trip through a
+            //         [window][60] tile so that the block leaves as contiguous 16-byte stores.  (Round 1 ran one warp per
+            //         window with 20 of its 32 lanes active: 165 warp-instructions per window, 14 % of the kernel.)
+            //         The power buffer is free from here to the next tile's stage 4 and provides the scratch.
             const bool last = a + nf >= f_hi;
             const uint32_t lim = last ? sg.w_end : min(sg.w_end, a + nf - 2);
-            for (uint32_t w = emit_next + warp; w < lim; w += kWarps) {
-                const int j = lane;
+            float* s_red = s_P;                               // [2][kMfcc][32] partial sums of x and x^2
+            float* s_mom = s_P + 2 * kMfcc * kTile;           // [2][32] sum x, sum x^2 per window
+            float* s_rows = s_P + 2 * kMfcc * kTile + 2 * kTile;   // [32][60] normalised rows (16-byte aligned)
+            for (uint32_t wb = emit_next; wb < lim; wb += kTile) {
+                const uint32_t w = wb + lane;
+                const bool live = w < lim;
+                const uint32_t w_hi = min(lim, wb + kTile);
+                const bool interior = wb >= 2 && w_hi + 2 <= n_total;            // block-uniform: no index clamps needed
                 float c0 = 0.f, d1 = 0.f, d2 = 0.f;
-                if (j < kMfcc) {
-                    const int hi = int(n_total) - 1;
-                    const float* rj = s_ring + j * kRingStride;
-                    auto cl = [hi](int x) { return min(max(x, 0), hi); };
+                {
+                    const float* rj = s_ring + warp * kRingStride;
                     auto C = [rj](int g) { return rj[g & (kRing - 1)]; };
-#ifdef SZB_TAIL_INTERIOR_FAST_PATH
-                    // EXPERIMENT for the next round (not compiled by default, not yet run): away from the clip's edges no
-                    // index clamps and 5 distinct ring loads instead of 9 (same operations on the same values: same bits)
-                    if (w >= 2 && int(w) + 2 <= hi) {                              // warp-uniform
+                    if (interior) {                                // same operations on the same values as below: same bits
                         const float m2 = C(int(w) - 2), m1 = C(int(w) - 1), p1 = C(int(w) + 1), p2 = C(int(w) + 2);
                         c0 = C(int(w));
-                        d1 = (p1 - m1) * 0.5f;
-                        d2 = ((p2 - c0) * 0.5f - (c0 - m2) * 0.5f) * 0.5f;
-                    } else
-#endif
-                    {
-                    const int ip = cl(int(w) + 1), im = cl(int(w) - 1);
-                    c0 = C(int(w));
-                    d1 = (C(ip) - C(im)) * 0.5f;                                   // lib.rs:223
-                    const float dp = (C(cl(ip + 1)) - C(cl(ip - 1))) * 0.5f;       // delta at clamp(w+1)
-                    const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;       // delta at clamp(w-1)
-                    d2 = (dp - dm) * 0.5f;                                         // lib.rs:322
+                        d1 = (p1 - m1) * 0.5f;                                     // lib.rs:223
+                        d2 = ((p2 - c0) * 0.5f - (c0 - m2) * 0.5f) * 0.5f;         // lib.rs:322
+                    } else if (live) {
+                        const int hi = int(n_total) - 1;
+                        auto cl = [hi](int x) { return min(max(x, 0), hi); };
+                        const int ip = cl(int(w) + 1), im = cl(int(w) - 1);
+                        c0 = C(int(w));
+                        d1 = (C(ip) - C(im)) * 0.5f;                               // lib.rs:223
+                        const float dp = (C(cl(ip + 1)) - C(cl(ip - 1))) * 0.5f;   // delta at clamp(w+1)
+                        const float dm = (C(cl(im + 1)) - C(cl(im - 1))) * 0.5f;   // delta at clamp(w-1)
+                        d2 = (dp - dm) * 0.5f;                                     // lib.rs:322
                     }
                 }
-                float sum = c0 + d1 + d2;
+                s_red[warp * kTile + lane] = c0 + d1 + d2;
+                s_red[(kMfcc + warp) * kTile + lane] = fmaf(c0, c0, fmaf(d1, d1, d2 * d2));
+                __syncthreads();
+                if (uwarp < 2) {                                   // warp 0: sum x, warp 1: sum x^2 (fixed order)
+                    const float* r = s_red + uwarp * kMfcc * kTile + lane;
+                    float acc0 = r[0], acc1 = r[kTile];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const float mean = sum * (1.f / float(kFeat));                     // lib.rs:328
-                const float e0 = c0 - mean, e1 = d1 - mean, e2 = d2 - mean;
-                float sq = j < kMfcc ? fmaf(e0, e0, fmaf(e1, e1, e2 * e2)) : 0.f;   // two-pass variance, lib.rs:329-336
-#pragma unroll
-                for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                // 1 / max(sqrt(var), 1e-6) (lib.rs:337) as min(rsqrt(var), 1e6): one 2-ulp reciprocal square root and three
-                // multiplies per lane instead of a square root and five IEEE divisions -- this stage was 17 % of the
-                // kernel's instructions; the difference (< 3e-7 relative) is far inside the 1e-4 parity tolerance
-                const float inv = fminf(rsqrtf(sq * (1.f / float(kFeat))), 1e6f);
-                if (j < kMfcc) {
-                    float* row = out_clip + size_t(w) * kFeat;
-                    row[j] = e0 * inv;                                             // lib.rs:338-340
-                    row[kMfcc + j] = e1 * inv;
-                    row[2 * kMfcc + j] = e2 * inv;
+                    for (int j = 2; j < kMfcc; j += 2) { acc0 += r[j * kTile]; acc1 += r[(j + 1) * kTile]; }
+                    s_mom[uwarp * kTile + lane] = acc0 + acc1;
                 }
+                __syncthreads();
+                // mean and population variance over the 60 values (lib.rs:328-336).  var = E[x^2] - mean^2: c0 carries most
+                // of E[x^2] and of the variance alike (the deltas average out near zero), so the subtraction loses no digits
+                // that matter at the 1e-4 parity bar (measured against the float64 oracle: unchanged 1-3e-6);
+                // 1 / max(sqrt(var), 1e-6) (lib.rs:337) as min(rsqrt(var), 1e6).
+                const float mean = s_mom[lane] * (1.f / float(kFeat));
+                const float var = fmaxf(fmaf(-mean, mean, s_mom[kTile + lane] * (1.f / float(kFeat))), 0.f);
+                const float inv = fminf(rsqrtf(var), 1e6f);
+                float* row = s_rows + lane * kFeat + warp;
+                row[0] = (c0 - mean) * inv;                                        // lib.rs:338-340
+                row[kMfcc] = (d1 - mean) * inv;
+                row[2 * kMfcc] = (d2 - mean) * inv;
+                __syncthreads();
+                {   // rows wb .. w_hi - 1 are contiguous in the output: (w_hi - wb) * 15 sixteen-byte chunks
+                    const int n_vec = int(w_hi - wb) * (kFeat / 4);
+                    float4* dst = reinterpret_cast<float4*>(out_clip + size_t(wb) * kFeat);
+                    const float4* src = reinterpret_cast<const float4*>(s_rows);
+                    if (tid < n_vec) dst[tid] = src[tid];
+                }
+                // (the next pass of this loop, or the next tile's stage 4, writes the scratch only after further barriers)
+                if (wb + kTile < lim) __syncthreads();
             }
             emit_next = max(emit_next, lim);
         }
@@ -369,6 +386,14 @@ __device__ __forceinline__ void res_issue(const int16_t* x, int64_t n_in, int64_
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(in ? x + gs : x), "r"(bytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// clamp to [-32768, 32767] and truncate toward zero (lib.rs:205-208) in ONE conversion: a float -> s16 cvt saturates at the
+// ends of the destination range (two FMNMX fewer per output sample than clamping in float first; same bits)
+__device__ __forceinline__ int16_t f32_to_s16_sat_rz(float v) {
+    short r;
+    asm("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return r;
 }
 
 template <int K, int D>   // K adjacent outputs per thread, whose windows start at most D input samples apart
@@ -477,7 +502,7 @@ resample_kernel(const int16_t* __restrict__ in, const uint64_t* __restrict__ in_
                     }
                     int16_t* so = s_out + shift + r * Lb + K * g;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) so[k] = int16_t(__float2int_rz(fminf(fmaxf(acc[k], -32768.f), 32767.f)));
+                    for (int k = 0; k < K; ++k) so[k] = f32_to_s16_sat_rz(acc[k]);
                 }
             }
             __syncthreads();
