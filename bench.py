@@ -134,14 +134,21 @@ class ClockSampler:
 
 
 # ---- reference arm / cpu baseline: the oracle's C restatement on the host cores ------------------------------------------
-def cpu_reference_rate(n_clips_sample, threads, steps=1, warmup=0, seed=1):
-    """audio-seconds/s of the restated reference CPU path (resample 16k->44.1k + extract) on `n_clips_sample` clips."""
+CPU_MODES = {0: "scalar FFT-800 (as oracle.c was timed in round 1)",
+             1: "FFT-800 vectorised 8 frames wide (AVX2, rustfft-class), mel / DCT per frame in the reference's sequential sum order",
+             2: "FFT, power and mel batched 8 frames wide -- stronger than the reference's own loops"}
+
+
+def cpu_reference_rate(n_clips_sample, threads, steps=1, warmup=0, seed=1, mode=1):
+    """audio-seconds/s of the restated reference CPU path (resample 16k->44.1k + extract) on `n_clips_sample` clips.
+    mode: see CPU_MODES (oracle.c so_set_mode); 1 is the arm the speed-up is quoted against."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import streamz_oracle as orc  # bench's cpu_baseline / reference leg is allowed to run the oracle
     so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
     if not os.path.exists(so):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
     lib = C.CDLL(so)
+    lib.so_set_mode(C.c_int(mode))
     n = RATE * CLIP_SECONDS
     base = [orc.synth_clip(s, 1000 + s, CLIP_SECONDS, rate=RATE) for s in range(min(8, n_clips_sample))]
     pcm = np.concatenate([base[i % len(base)] for i in range(n_clips_sample)])
@@ -197,11 +204,32 @@ def cpu_mlp_rate(n_windows, speakers, batch, seed=3):
     return n_windows / dt, dt, int(used)
 
 
-def cpu_sample_for(seconds, threads, cap):
+def cpu_sample_for(seconds, threads, cap, mode=1):
     """Number of clips whose CPU extraction takes about `seconds` on this host (probe with a few clips per thread first)."""
     probe = int(min(cap, max(16, threads * 4)))
-    rate, _ = cpu_reference_rate(probe, threads)
+    rate, _ = cpu_reference_rate(probe, threads, mode=mode)
     return int(min(cap, max(probe, rate * seconds / CLIP_SECONDS)))
+
+
+def cpu_baseline_block(cores, seconds, cap):
+    """cpu_baseline of the extraction metric: the arm the ratio is quoted against (mode 1) plus the scalar and the fully
+    batched variants on short samples, each with its per-core cost, so the "x" beside it can be read for what it is."""
+    wins_per_clip = 1101
+    sample = cpu_sample_for(seconds, cores, cap, mode=1)
+    rate, dt = cpu_reference_rate(sample, cores, steps=1, warmup=0, mode=1)
+    out = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+           "us_per_window_per_core": dt * cores / (sample * wins_per_clip) * 1e6,
+           "sample": f"{sample} of {cap} clips, C restatement of lib.rs:186-345 (oracle/oracle.c), one clip per thread, {dt:.2f} s; "
+                     + CPU_MODES[1], "variants": {}}
+    for mode in (0, 2):
+        try:
+            smp = cpu_sample_for(min(3.0, seconds), cores, cap, mode=mode)
+            r, d = cpu_reference_rate(smp, cores, steps=1, warmup=0, mode=mode)
+            out["variants"]["scalar" if mode == 0 else "batched"] = {
+                "value": r, "us_per_window_per_core": d * cores / (smp * wins_per_clip) * 1e6, "sample": f"{smp} clips, {d:.2f} s; " + CPU_MODES[mode]}
+        except Exception as e:
+            out["variants"][str(mode)] = {"error": repr(e)}
+    return out
 
 
 def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
@@ -331,14 +359,15 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     # bounded sample: about 3 s of host work per step keeps K + W steps within a couple of minutes on any host
     sample = cpu_sample_for(3.0, cores, N_CLIPS)
-    rate, dt = cpu_reference_rate(sample, cores, steps=args.steps, warmup=args.warmup)
+    rate, dt = cpu_reference_rate(sample, cores, steps=args.steps, warmup=args.warmup, mode=1)
     line = {"impl": "reference", "metric": "audio-seconds/sec MFCC+delta extraction", "value": rate, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"extract {N_CLIPS} x {CLIP_SECONDS}-s clips 16k->44.1k (BASELINE configs[1]); each step = "
                                    f"{sample}-clip sample of it on the host CPU", "clips_per_step": sample},
             "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} of {N_CLIPS} clips per step, C restatement of lib.rs:186-345, one clip per thread"},
+                             "us_per_window_per_core": dt * cores / (sample * 1101) * 1e6,
+                             "sample": f"{sample} of {N_CLIPS} clips per step, C restatement of lib.rs:186-345, one clip per thread; " + CPU_MODES[1]},
             "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print_line(line)
     return 0
@@ -362,9 +391,15 @@ def main():
     ap.add_argument("--no-mlp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--config", default="c2", choices=["c2", "c1", "c4", "c5"],
+                    help="c2 (default): BASELINE configs[1] + configs[2], the driver's line; c1 / c4 / c5: the other BASELINE configs "
+                         "(configs[0], [3], [4]), each printing its own JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c2":
+        import bench_configs
+        return bench_configs.run(args, print_line)
 
     import torch
     import torch.distributed as dist
@@ -475,11 +510,17 @@ def main():
         return 0
 
     peak, peak_src = measured_peaks()
-    windows_per_launch = total
+    launches_per_step = max(1, int(round(k_n / max(1, args.steps))))
+    windows_per_launch = total // launches_per_step
     algo_bytes = windows_per_launch * BYTES_PER_WINDOW_44K
     k_avg_ms = k_ms / max(1, k_n)
     achieved = algo_bytes / (k_avg_ms * 1e-3) / 1e9 if k_n else None
     traffic, traffic_src = measured_traffic("extract_kernel", windows_per_launch)
+    # the whole step (resample + extract) against SURVEY.md 8(d)'s fused figure: 2 r + 26 460 bytes per audio-second
+    step_algo = BYTES_PER_AUDIO_S_FUSED * audio_s
+    step_achieved = step_algo / (ms_per_step * 1e-3) / 1e9
+    rs_traffic, _ = measured_traffic("resample_kernel", total)
+    step_traffic = (traffic * launches_per_step + rs_traffic) if (traffic and rs_traffic) else None
     line = {
         "metric": "audio-seconds/sec MFCC+delta extraction", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -493,16 +534,19 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "kernel": "extract_kernel", "launch_ms": k_avg_ms, "launches_timed": int(k_n),
                      "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
-                     "note": "1040 B/window (800 read + 240 written) x windows per launch / CUDA-event launch time"},
+                     "note": "1040 B/window (800 read + 240 written) x windows per launch / CUDA-event launch time",
+                     "step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_step": int(step_algo),
+                              "traffic": step_traffic, "ms": ms_per_step,
+                              "note": "whole step (resample_kernel + extract_kernel) against the fused figure of SURVEY.md 8(d), "
+                                      "58 460 B per audio-second at 16 kHz; traffic = measured DRAM bytes of both kernels: the 44.1 kHz "
+                                      "i16 intermediate makes one round trip through HBM (DESIGN.md 5: fusing it away was measured "
+                                      "slower, neither kernel is HBM-bound)"}},
         "clocks": clocks, "mlp": mlp,
     }
     if not args.no_cpu and world >= 1:
         cores = os.cpu_count() or 1
         try:
-            sample = cpu_sample_for(12.0, cores, n_clips)      # about 10-30 s of CPU work, bounded by the workload itself
-            rate, dt = cpu_reference_rate(sample, cores, steps=1, warmup=0)
-            line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} of {n_clips} clips, C restatement of lib.rs:186-345 (oracle/oracle.c), one clip per thread, {dt:.2f} s"}
+            line["cpu_baseline"] = cpu_baseline_block(cores, 10.0, n_clips)   # about 10 s + 2 x 3 s of CPU work
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
         if isinstance(mlp, dict) and "error" not in mlp and rank == 0:

@@ -135,6 +135,145 @@ void so_fft800(const float* in_re, float* out_re, float* out_im) { /* exported f
     for (int i = 0; i < WIN; ++i) { out_re[i] = a[i].re; out_im[i] = a[i].im; }
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* Hardened CPU arm: the same Stockham passes with LANE = FRAME.  The scalar fft800 above runs at ~9 us per frame,     */
+/* several times slower than rustfft's AVX butterflies would; here VL frames travel through every butterfly together   */
+/* (structure of arrays: element e of lane l at [e * VL + l]), so the inner loops are unit-stride and gcc turns them    */
+/* into AVX2 / AVX-512 arithmetic (check: make -C oracle vecreport).  Per frame the operations and their order are      */
+/* exactly those of the scalar passes.  so_set_mode: 0 = scalar (as written), 1 = SIMD FFT, mel / DCT per frame in the  */
+/* reference's sequential summation order (the default of the timed baseline: closest to what the Rust binary does:     */
+/* rustfft is SIMD, `iter().zip().map().sum()` is not), 2 = mel and DCT batched over the lanes too (a stronger baseline */
+/* than the reference itself).                                                                                          */
+/* ---------------------------------------------------------------------------------------------------------------- */
+#define VL 8
+static int g_mode = 1;
+void so_set_mode(int mode) { g_mode = mode; }
+int so_get_mode(void) { return g_mode; }
+
+typedef struct { float* re; float* im; } vbuf;   /* [WIN * VL] each */
+
+#define VLOOP for (int l = 0; l < VL; ++l)
+typedef float vf __attribute__((vector_size(VL * 4), aligned(4)));   /* GCC vector extension: one value per frame */
+#define VLD(ptr, e) (*(const vf*)((ptr) + (size_t)(e) * VL))
+#define VST(ptr, e) (*(vf*)((ptr) + (size_t)(e) * VL))
+
+static void vpass_r5(vbuf x, vbuf y, int n, int s) {
+    const int m = n / (s * 5);
+    const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+    for (int p = 0; p < m; ++p) {
+        const int twstep = WIN / (m * 5);
+        const cpx w1 = g_tw[(p * twstep) % WIN], w2 = g_tw[(2 * p * twstep) % WIN], w3 = g_tw[(3 * p * twstep) % WIN],
+                  w4 = g_tw[(4 * p * twstep) % WIN];
+        for (int q = 0; q < s; ++q) {
+            const int i0 = q + s * p, i1 = q + s * (p + m), i2 = q + s * (p + 2 * m), i3 = q + s * (p + 3 * m), i4 = q + s * (p + 4 * m);
+            const vf x0r = VLD(x.re, i0), x0i = VLD(x.im, i0), x1r = VLD(x.re, i1), x1i = VLD(x.im, i1), x2r = VLD(x.re, i2),
+                     x2i = VLD(x.im, i2), x3r = VLD(x.re, i3), x3i = VLD(x.im, i3), x4r = VLD(x.re, i4), x4i = VLD(x.im, i4);
+            const vf t1r = x1r + x4r, t1i = x1i + x4i, t2r = x2r + x3r, t2i = x2i + x3i;
+            const vf t3r = x1r - x4r, t3i = x1i - x4i, t4r = x2r - x3r, t4i = x2i - x3i;
+            const vf a1r = x0r + c1 * t1r + c2 * t2r, a1i = x0i + c1 * t1i + c2 * t2i;
+            const vf a2r = x0r + c2 * t1r + c1 * t2r, a2i = x0i + c2 * t1i + c1 * t2i;
+            const vf b1r = s1 * t3r + s2 * t4r, b1i = s1 * t3i + s2 * t4i;
+            const vf b2r = s2 * t3r - s1 * t4r, b2i = s2 * t3i - s1 * t4i;
+            const vf u1r = a1r + b1i, u1i = a1i - b1r, u4r = a1r - b1i, u4i = a1i + b1r;
+            const vf u2r = a2r + b2i, u2i = a2i - b2r, u3r = a2r - b2i, u3i = a2i + b2r;
+            const int o = q + s * 5 * p;
+            VST(y.re, o) = x0r + t1r + t2r;                      VST(y.im, o) = x0i + t1i + t2i;
+            VST(y.re, o + s) = u1r * w1.re - u1i * w1.im;        VST(y.im, o + s) = u1r * w1.im + u1i * w1.re;
+            VST(y.re, o + 2 * s) = u2r * w2.re - u2i * w2.im;    VST(y.im, o + 2 * s) = u2r * w2.im + u2i * w2.re;
+            VST(y.re, o + 3 * s) = u3r * w3.re - u3i * w3.im;    VST(y.im, o + 3 * s) = u3r * w3.im + u3i * w3.re;
+            VST(y.re, o + 4 * s) = u4r * w4.re - u4i * w4.im;    VST(y.im, o + 4 * s) = u4r * w4.im + u4i * w4.re;
+        }
+    }
+}
+static void vpass_r4(vbuf x, vbuf y, int n, int s) {
+    const int m = n / (s * 4);
+    for (int p = 0; p < m; ++p) {
+        const int twstep = WIN / (m * 4);
+        const cpx w1 = g_tw[(p * twstep) % WIN], w2 = g_tw[(2 * p * twstep) % WIN], w3 = g_tw[(3 * p * twstep) % WIN];
+        for (int q = 0; q < s; ++q) {
+            const int i0 = q + s * p, i1 = q + s * (p + m), i2 = q + s * (p + 2 * m), i3 = q + s * (p + 3 * m);
+            const vf ar = VLD(x.re, i0), ai = VLD(x.im, i0), br = VLD(x.re, i1), bi = VLD(x.im, i1), cr = VLD(x.re, i2), ci = VLD(x.im, i2),
+                     dr = VLD(x.re, i3), di = VLD(x.im, i3);
+            const vf apcr = ar + cr, apci = ai + ci, amcr = ar - cr, amci = ai - ci, bpdr = br + dr, bpdi = bi + di;
+            const vf bmdr = bi - di, bmdi = dr - br;                                /* (b - d) * (-i) */
+            const vf u1r = amcr + bmdr, u1i = amci + bmdi, u2r = apcr - bpdr, u2i = apci - bpdi, u3r = amcr - bmdr, u3i = amci - bmdi;
+            const int o = q + s * 4 * p;
+            VST(y.re, o) = apcr + bpdr;                          VST(y.im, o) = apci + bpdi;
+            VST(y.re, o + s) = u1r * w1.re - u1i * w1.im;        VST(y.im, o + s) = u1r * w1.im + u1i * w1.re;
+            VST(y.re, o + 2 * s) = u2r * w2.re - u2i * w2.im;    VST(y.im, o + 2 * s) = u2r * w2.im + u2i * w2.re;
+            VST(y.re, o + 3 * s) = u3r * w3.re - u3i * w3.im;    VST(y.im, o + 3 * s) = u3r * w3.im + u3i * w3.re;
+        }
+    }
+}
+static void vpass_r2(vbuf x, vbuf y, int n, int s) {
+    const int m = n / (s * 2);
+    for (int p = 0; p < m; ++p) {
+        const cpx w1 = g_tw[(p * (WIN / (m * 2))) % WIN];
+        for (int q = 0; q < s; ++q) {
+            const int i0 = q + s * p, i1 = q + s * (p + m), o = q + s * 2 * p;
+            const vf ar = VLD(x.re, i0), ai = VLD(x.im, i0), br = VLD(x.re, i1), bi = VLD(x.im, i1);
+            const vf ur = ar - br, ui = ai - bi;
+            VST(y.re, o) = ar + br;                              VST(y.im, o) = ai + bi;
+            VST(y.re, o + s) = ur * w1.re - ui * w1.im;          VST(y.im, o + s) = ur * w1.im + ui * w1.re;
+        }
+    }
+}
+/* VL frames at once; returns the buffer that holds the result (a or b) */
+static vbuf vfft800(vbuf a, vbuf b) {
+    pthread_once(&g_tw_once, init_tw);
+    vbuf x = a, y = b;
+    int s = 1;
+    static const int radices[5] = { 5, 5, 4, 4, 2 };
+    for (int i = 0; i < 5; ++i) {
+        const int R = radices[i];
+        if (R == 4) vpass_r4(x, y, WIN, s);
+        else if (R == 2) vpass_r2(x, y, WIN, s);
+        else vpass_r5(x, y, WIN, s);
+        s *= R;
+        vbuf t = x; x = y; y = t;
+    }
+    return x;
+}
+
+/* MFCCs of windows [w0, w0 + VL) (lanes past n repeat the last window; their results are dropped by the caller) */
+static void mfcc_group(const int16_t* pcm, size_t n, size_t w0, const float* mel, const float* dct, vbuf a, vbuf b, float* mags,
+                       float* base) {
+    for (int l = 0; l < VL; ++l) {
+        const size_t w = w0 + (size_t)l < n ? w0 + (size_t)l : n - 1;
+        const int16_t* chunk = pcm + w * HOP;
+        for (int i = 0; i < WIN; ++i) { a.re[(size_t)i * VL + l] = (float)chunk[i] / 32767.0f; a.im[(size_t)i * VL + l] = 0.f; }  /* lib.rs:293-295 */
+    }
+    const vbuf r = vfft800(a, b);                                                                  /* lib.rs:296 */
+    for (int k = 0; k < NBINS; ++k) VST(mags, k) = VLD(r.re, k) * VLD(r.re, k) + VLD(r.im, k) * VLD(r.im, k);
+    float energies[NMEL][VL];
+    if (g_mode >= 2) {                        /* all lanes walk the 401 bins together: same order per frame, SIMD across frames */
+        for (int m = 0; m < NMEL; ++m) {
+            vf sum = { 0.f };
+            const float* filt = mel + (size_t)m * NBINS;
+            for (int k = 0; k < NBINS; ++k) sum += filt[k] * VLD(mags, k);
+            VLOOP energies[m][l] = logf(fmaxf(sum[l], 1e-12f));
+        }
+    } else {                                  /* one frame at a time, sequential sum: what `.zip().map().sum()` compiles to */
+        float one[NBINS];                     /* this frame's mags, contiguous like the reference's per-window Vec (lib.rs:297) */
+        for (int l = 0; l < VL; ++l) {
+            for (int k = 0; k < NBINS; ++k) one[k] = mags[(size_t)k * VL + l];
+            for (int m = 0; m < NMEL; ++m) {
+                float sum = 0.f;
+                const float* filt = mel + (size_t)m * NBINS;
+                for (int k = 0; k < NBINS; ++k) sum += filt[k] * one[k];                          /* lib.rs:304-308 */
+                energies[m][l] = logf(fmaxf(sum, 1e-12f));                                       /* lib.rs:309 */
+            }
+        }
+    }
+    for (int l = 0; l < VL && w0 + (size_t)l < n; ++l)
+        for (int j = 0; j < NMFCC; ++j) {                                                         /* lib.rs:312-314 */
+            float acc = 0.f;
+            for (int m = 0; m < NMEL; ++m) acc += dct[j * NMEL + m] * energies[m][l];
+            base[(w0 + (size_t)l) * NMFCC + j] = acc;
+        }
+}
+
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* Front end (lib.rs:279-345)                                                                                        */
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -148,6 +287,13 @@ size_t so_extract(const int16_t* pcm, size_t len, const float* mel, const float*
     cpx* buffer = (cpx*)malloc(sizeof(cpx) * WIN);           /* lib.rs:285 */
     cpx* scratch = (cpx*)malloc(sizeof(cpx) * WIN);
     float* base = (float*)malloc(sizeof(float) * n * NMFCC);
+    if (g_mode >= 1) {
+        vbuf a = { (float*)aligned_alloc(64, sizeof(float) * WIN * VL), (float*)aligned_alloc(64, sizeof(float) * WIN * VL) };
+        vbuf b = { (float*)aligned_alloc(64, sizeof(float) * WIN * VL), (float*)aligned_alloc(64, sizeof(float) * WIN * VL) };
+        float* vmags = (float*)aligned_alloc(64, sizeof(float) * ((NBINS * VL + 15) / 16 * 16));
+        for (size_t w0 = 0; w0 < n; w0 += VL) mfcc_group(pcm, n, w0, mel, dct, a, b, vmags, base);
+        free(a.re); free(a.im); free(b.re); free(b.im); free(vmags);
+    } else
     for (size_t w = 0; w < n; ++w) {                          /* lib.rs:291 */
         const int16_t* chunk = pcm + w * HOP;
         for (int i = 0; i < WIN; ++i) { buffer[i].re = (float)chunk[i] / 32767.0f; buffer[i].im = 0.f; } /* lib.rs:293-295 */
@@ -202,10 +348,10 @@ size_t so_extract(const int16_t* pcm, size_t len, const float* mel, const float*
 size_t so_resample(const int16_t* in, size_t n_in, uint32_t rate, const float* taps, uint32_t L, uint32_t M, uint32_t T,
                    int16_t* out) {
     size_t n_out = (size_t)(((unsigned long long)n_in * 44100ull) / rate);
-    for (size_t j = 0; j < n_out; ++j) {
-        unsigned long long pos = (unsigned long long)j * M;
-        long long i0 = (long long)(pos / L);
-        uint32_t p = (uint32_t)(pos % L);
+    long long i0 = 0;
+    uint32_t p = 0;                              /* j M = i0 L + p, advanced incrementally (M may exceed L) */
+    for (size_t j = 0; j < n_out; ++j, p += M) {
+        while (p >= L) { p -= L; ++i0; }
         const float* c = taps + (size_t)p * T;
         float acc = 0.f;
         for (uint32_t t = 0; t < T; ++t) {

@@ -56,6 +56,9 @@ def summary(rep, header):
         for k in RAW:
             if k in head:
                 print(f"  {k:90s} {v[head.index(k)]} {units[head.index(k)]}")
+        for j, k in enumerate(head):                         # tensor pipe (tcgen05) and TMEM / uniform-datapath counters, whatever this ncu names them
+            if ("pipe_tensor" in k or "pipe_tmem" in k) and ".avg" in k and "Triage" not in k and k not in RAW and v[j] not in ("", "0", "n/a"):
+                print(f"  {k:90s} {v[j]} {units[j]}")
         print("  -- warp stalls per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active)")
         st = [(float(v[j]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for j, h in enumerate(head)
               if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and v[j]]
