@@ -248,6 +248,10 @@ szb_status szb_net_embedding_mean(szb_net* net, const float* feats, uint64_t n_w
 szb_status szb_net_embedding_median(szb_net* net, const float* feats, uint64_t n_windows, int32_t relu2, float* out);
 /* cosine_similarity (lib.rs:1531-1540) */
 float szb_cosine_similarity(const float* a, const float* b, uint32_t n);
+/* identify_speaker_from_embedding (lib.rs:1503-1529): best cosine match among n centroids [n][dim] (ids may be NULL: 0..n-1);
+ * *best_id = UINT64_MAX (usize::MAX) when the best similarity does not exceed the threshold (x 0.7 below 20 speakers). */
+szb_status szb_match_embedding(const float* emb, const float* centroids, const uint64_t* ids, uint32_t n, uint32_t dim,
+                               float threshold, uint64_t* best_id, float* best_sim);
 
 /* ---- multi-GPU: batch-parallel training, one NCCL all-reduce of the flattened gradient per step --------------------- */
 szb_status szb_comm_unique_id(uint8_t id[128]);

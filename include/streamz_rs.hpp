@@ -25,6 +25,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <tuple>
 #include <vector>
 
 #include "streamz_b200.h"
@@ -179,6 +180,28 @@ class SimpleNeuralNet {   // lib.rs:745-1282
         const std::vector<float> flat = detail::flatten(batch, input_size());
         check(szb_net_train_batch(net_, flat.data(), batch.size(), target.data(), lr));
     }
+    // set_embeddings / embeddings (lib.rs:869-877): (embedding, mean similarity, std similarity) per speaker, saved with the model
+    using SpeakerEmbedding = std::tuple<std::vector<float>, float, float>;
+    void set_embeddings(const std::vector<SpeakerEmbedding>& embeds) {
+        const size_t dim = embeds.empty() ? 0 : std::get<0>(embeds[0]).size();
+        std::vector<float> flat, mean, sd;
+        for (const auto& e : embeds) {
+            flat.insert(flat.end(), std::get<0>(e).begin(), std::get<0>(e).end());
+            mean.push_back(std::get<1>(e));
+            sd.push_back(std::get<2>(e));
+        }
+        check(szb_net_set_embeddings(net_, flat.data(), mean.data(), sd.data(), uint32_t(embeds.size()), uint32_t(dim)));
+    }
+    std::vector<SpeakerEmbedding> embeddings() const {
+        uint32_t n = 0, dim = 0;
+        check(szb_net_get_embeddings(net_, nullptr, nullptr, nullptr, 0, &n, &dim));
+        std::vector<float> flat(size_t(n) * dim), mean(n), sd(n);
+        if (n) check(szb_net_get_embeddings(net_, flat.data(), mean.data(), sd.data(), n, &n, &dim));
+        std::vector<SpeakerEmbedding> out;
+        for (uint32_t i = 0; i < n; ++i)
+            out.emplace_back(std::vector<float>(flat.begin() + size_t(i) * dim, flat.begin() + size_t(i + 1) * dim), mean[i], sd[i]);
+        return out;
+    }
     void save(const std::string& path) const { check(szb_net_save(net_, path.c_str(), sample_rate_, bits_)); }   // lib.rs:1081
     static SimpleNeuralNet load(const std::string& path) {   // lib.rs:1132
         SimpleNeuralNet n;
@@ -238,6 +261,41 @@ inline float pretrain_from_features(SimpleNeuralNet& net, const Windows& windows
     szb_dev_free(ctx, d_feats);
     szb_dev_free(ctx, d_labels);
     return count ? float(total / double(count)) : 0.0f;   // lib.rs:623-627
+}
+
+// lib.rs:348-397: `epochs` times augment -> extract -> shuffle -> dropout / train_batch chunks; one device-resident C call.
+// Every draw the reference takes from thread_rng (augmentation, shuffle, dropout) derives from `seed` (szb_loop_seed).
+inline float pretrain_network(SimpleNeuralNet& net, const std::vector<int16_t>& samples, size_t target_class, size_t num_classes,
+                              size_t epochs, float lr, float dropout, size_t batch_size, uint64_t seed = 0) {
+    if (num_classes != net.output_size()) throw Error(SZB_ERR_INVALID, "pretrain_network: num_classes != output_size");
+    double loss = 0.0;
+    uint64_t used = 0;
+    check(szb_net_pretrain_network(net.handle(), samples.data(), samples.size(), uint32_t(target_class), uint32_t(epochs), lr, dropout,
+                                   uint32_t(batch_size ? batch_size : 1), seed, &loss, &used));
+    return used ? float(loss / double(used)) : 0.0f;   // lib.rs:392-396
+}
+
+// lib.rs:668-732 on decoded 44.1 kHz clips (decoding stays with the caller, lib.rs:696): every (file, epoch) is one
+// pretrain_network epoch at lr * 0.99^step (lib.rs:708-709), file-major; records the training files (lib.rs:723).
+struct TrainingClip { std::string path; std::vector<int16_t> samples; size_t cls; };
+inline float train_from_files(SimpleNeuralNet& net, const std::vector<TrainingClip>& files, size_t num_speakers, size_t epochs, float lr,
+                              float dropout, size_t batch_size, uint64_t seed = 0) {
+    if (num_speakers != net.output_size()) throw Error(SZB_ERR_INVALID, "train_from_files: num_speakers != output_size");
+    net.set_dataset_specs(DEFAULT_SAMPLE_RATE, 16);   // lib.rs:703-706
+    std::vector<int16_t> pcm;
+    std::vector<uint64_t> off{ 0 };
+    std::vector<uint32_t> classes;
+    for (const auto& f : files) {
+        pcm.insert(pcm.end(), f.samples.begin(), f.samples.end());
+        off.push_back(pcm.size());
+        classes.push_back(uint32_t(f.cls));
+    }
+    double loss = 0.0;
+    uint64_t used = 0;
+    check(szb_net_train_from_files(net.handle(), pcm.data(), off.data(), classes.data(), uint32_t(files.size()), uint32_t(epochs), lr, dropout,
+                                   uint32_t(batch_size ? batch_size : 1), seed, &loss, &used));
+    for (const auto& f : files) net.record_training_file(f.cls, f.path);
+    return used ? float(loss / double(used)) : 0.0f;
 }
 
 // lib.rs:632-665: files one after the other, each for all its epochs; mean of the per-file losses.

@@ -61,6 +61,14 @@ extern "C" {
     fn szb_identify_speaker_list(net: *mut SzbNet, pcm: *const i16, n: u64, thr: f32, out: *mut u32, cap: u32, n_out: *mut u32) -> c_int;
     fn szb_net_save(net: *mut SzbNet, path: *const c_char, sample_rate: u32, bits: u32) -> c_int;
     fn szb_net_load(ctx: *mut SzbCtx, path: *const c_char, out: *mut *mut SzbNet, sr: *mut u32, bits: *mut u32) -> c_int;
+    fn szb_match_embedding(emb: *const f32, centroids: *const f32, ids: *const u64, n: u32, dim: u32, threshold: f32, best_id: *mut u64,
+                           best_sim: *mut f32) -> c_int;
+    fn szb_net_set_embeddings(net: *mut SzbNet, emb: *const f32, mean: *const f32, std: *const f32, n: u32, dim: u32) -> c_int;
+    fn szb_net_get_embeddings(net: *const SzbNet, emb: *mut f32, mean: *mut f32, std: *mut f32, cap_n: u32, n: *mut u32, dim: *mut u32) -> c_int;
+    fn szb_net_pretrain_network(net: *mut SzbNet, pcm: *const i16, n: u64, class: u32, epochs: u32, lr: f32, dropout: f32, batch: u32, seed: u64,
+                                loss: *mut f64, used: *mut u64) -> c_int;
+    fn szb_net_train_from_files(net: *mut SzbNet, pcm: *const i16, clip_off: *const u64, classes: *const u32, n_files: u32, epochs: u32, lr: f32,
+                                dropout: f32, batch: u32, seed: u64, loss: *mut f64, used: *mut u64) -> c_int;
 }
 
 fn check(status: c_int) -> Result<(), Box<dyn Error>> {
@@ -219,6 +227,27 @@ impl SimpleNeuralNet {
         let c = CString::new(path)?;
         check(unsafe { szb_net_save(self.net, c.as_ptr(), self.sample_rate, self.bits as u32) })
     }
+    /// lib.rs:869-872: (embedding, mean similarity, std similarity) per speaker; saved with the model (lib.rs:1114-1127)
+    pub fn set_embeddings(&mut self, embeds: Vec<(Vec<f32>, f32, f32)>) {
+        let dim = embeds.first().map(|e| e.0.len()).unwrap_or(0);
+        let flat: Vec<f32> = embeds.iter().flat_map(|e| e.0.iter().copied()).collect();
+        let mean: Vec<f32> = embeds.iter().map(|e| e.1).collect();
+        let std: Vec<f32> = embeds.iter().map(|e| e.2).collect();
+        check(unsafe { szb_net_set_embeddings(self.net, flat.as_ptr(), mean.as_ptr(), std.as_ptr(), embeds.len() as u32, dim as u32) })
+            .expect("set_embeddings");
+    }
+    /// lib.rs:874-877 (returned by value: the arrays live behind the C ABI)
+    pub fn embeddings(&self) -> Vec<(Vec<f32>, f32, f32)> {
+        let (mut n, mut dim) = (0u32, 0u32);
+        check(unsafe { szb_net_get_embeddings(self.net, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(), 0, &mut n, &mut dim) })
+            .expect("embeddings");
+        let (mut flat, mut mean, mut std) = (vec![0f32; (n * dim) as usize], vec![0f32; n as usize], vec![0f32; n as usize]);
+        if n > 0 {
+            check(unsafe { szb_net_get_embeddings(self.net, flat.as_mut_ptr(), mean.as_mut_ptr(), std.as_mut_ptr(), n, &mut n, &mut dim) })
+                .expect("embeddings");
+        }
+        (0..n as usize).map(|i| (flat[i * dim as usize..(i + 1) * dim as usize].to_vec(), mean[i], std[i])).collect()
+    }
     /// lib.rs:1132-1282
     pub fn load(path: &str) -> Result<Self, Box<dyn Error>> {
         let c = CString::new(path)?;
@@ -274,6 +303,49 @@ pub fn pretrain_from_features(net: &mut SimpleNeuralNet, windows: &[Vec<f32>], t
         szb_dev_free(ctx(), d_labels);
     }
     if count > 0 { (total / count as f64) as f32 } else { 0.0 }
+}
+
+/// lib.rs:348-397: per epoch augment -> extract -> shuffle -> dropout / train_batch chunks, one C call, device-resident.
+/// `_extractor` is kept for the reference's signature; the draws the reference takes from thread_rng derive from the clock.
+pub fn pretrain_network(net: &mut SimpleNeuralNet, samples: &[i16], target_class: usize, num_classes: usize, epochs: usize, lr: f32,
+                        dropout: f32, batch_size: usize, _extractor: &FeatureExtractor) -> f32 {
+    assert_eq!(num_classes, net.output_size());
+    let seed = std::time::SystemTime::now().duration_since(std::time::UNIX_EPOCH).map(|d| d.as_nanos() as u64).unwrap_or(0);
+    let (mut loss, mut used) = (0f64, 0u64);
+    check(unsafe {
+        szb_net_pretrain_network(net.net, samples.as_ptr(), samples.len() as u64, target_class as u32, epochs as u32, lr, dropout,
+                                 batch_size.max(1) as u32, seed, &mut loss, &mut used)
+    })
+    .expect("pretrain_network");
+    if used > 0 { (loss / used as f64) as f32 } else { 0.0 }
+}
+
+/// lib.rs:668-732 on already decoded clips (decode + resample stay with the caller, lib.rs:696): every (file, epoch) is one
+/// pretrain_network epoch at lr * 0.99^step; file-major order (one serialisation of the reference's rayon loop under its lock).
+pub fn train_from_files(net: std::sync::Arc<std::sync::RwLock<SimpleNeuralNet>>, files: &[(&str, &[i16], usize)], _total_files: usize,
+                        num_speakers: usize, epochs: usize, lr: f32, dropout: f32, batch_size: usize, _extractor: &FeatureExtractor)
+                        -> Result<(), Box<dyn Error>> {
+    let mut guard = net.write().map_err(|_| "poisoned lock")?;
+    assert_eq!(num_speakers, guard.output_size());
+    guard.sample_rate = DEFAULT_SAMPLE_RATE;                                       // lib.rs:703-706
+    guard.bits = 16;
+    let mut off = vec![0u64];
+    let mut pcm: Vec<i16> = Vec::new();
+    for (_, s, _) in files {
+        pcm.extend_from_slice(s);
+        off.push(pcm.len() as u64);
+    }
+    let classes: Vec<u32> = files.iter().map(|f| f.2 as u32).collect();
+    let seed = std::time::SystemTime::now().duration_since(std::time::UNIX_EPOCH).map(|d| d.as_nanos() as u64).unwrap_or(0);
+    let (mut loss, mut used) = (0f64, 0u64);
+    check(unsafe {
+        szb_net_train_from_files(guard.net, pcm.as_ptr(), off.as_ptr(), classes.as_ptr(), files.len() as u32, epochs as u32, lr, dropout,
+                                 batch_size.max(1) as u32, seed, &mut loss, &mut used)
+    })?;
+    for (path, _, class) in files {
+        guard.record_training_file(*class, path);                                   // lib.rs:723
+    }
+    Ok(())
 }
 
 /// lib.rs:632-665
@@ -382,18 +454,16 @@ pub fn extract_embedding(net: &SimpleNeuralNet, sample: &[i16], extractor: &Feat
 pub fn cosine_similarity(a: &[f32], b: &[f32]) -> f32 {
     unsafe { szb_cosine_similarity(a.as_ptr(), b.as_ptr(), a.len().min(b.len()) as u32) }
 }
-/// lib.rs:1503-1529 (`usize::MAX` when nothing passes the threshold, which is relaxed by 0.7 below 20 speakers)
+/// lib.rs:1503-1529; the matching rule runs behind the C ABI (`szb_match_embedding`), this wrapper only flattens the map.
 pub fn identify_speaker_from_embedding(emb: &[f32], speaker_embeddings: &std::collections::HashMap<usize, Vec<f32>>, threshold: f32) -> usize {
-    let (mut best_sim, mut best_id) = (f32::MIN, usize::MAX);
-    for (&id, centroid) in speaker_embeddings.iter() {
-        let sim = cosine_similarity(emb, centroid);
-        if sim > best_sim {
-            best_sim = sim;
-            best_id = id;
-        }
-    }
-    let dynamic = if speaker_embeddings.len() < 20 { threshold * 0.7 } else { threshold };
-    if best_sim > dynamic { best_id } else { usize::MAX }
+    let ids: Vec<u64> = speaker_embeddings.keys().map(|&k| k as u64).collect();
+    let flat: Vec<f32> = speaker_embeddings.values().flat_map(|v| v.iter().copied()).collect();
+    let mut found = u64::MAX;
+    check(unsafe {
+        szb_match_embedding(emb.as_ptr(), flat.as_ptr(), ids.as_ptr(), ids.len() as u32, emb.len() as u32, threshold, &mut found, std::ptr::null_mut())
+    })
+    .expect("match_embedding");
+    if found == u64::MAX { usize::MAX } else { found as usize }
 }
 /// lib.rs:103-116 with the draws derived from `seed` (the reference uses thread_rng)
 pub fn augment(samples: &[i16], seed: u64) -> Vec<i16> {

@@ -103,6 +103,7 @@ SIGNATURES = {
     "szb_net_embedding_mean": (i32, [vp, vp, u64, vp]),
     "szb_net_embedding_median": (i32, [vp, vp, u64, i32, vp]),
     "szb_cosine_similarity": (f32, [vp, vp, u32]),
+    "szb_match_embedding": (i32, [vp, vp, vp, u32, u32, f32, P(u64), P(f32)]),
     "szb_comm_unique_id": (i32, [vp]),
     "szb_comm_init": (i32, [vp, vp, i32, i32]),
     "szb_comm_destroy": (i32, [vp]),

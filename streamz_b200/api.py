@@ -674,14 +674,16 @@ def cosine_similarity(a, b) -> float:
 
 
 def identify_speaker_from_embedding(emb, speaker_embeddings: Dict[int, np.ndarray], threshold: float) -> Optional[int]:
-    """lib.rs:1503-1529 (``None`` stands for ``usize::MAX``)."""
-    best_sim, best_id = -np.inf, None
-    for sid, centroid in speaker_embeddings.items():
-        sim = cosine_similarity(emb, centroid)
-        if sim > best_sim:
-            best_sim, best_id = sim, sid
-    dyn = threshold * 0.7 if len(speaker_embeddings) < 20 else threshold
-    return best_id if best_sim > dyn else None
+    """lib.rs:1503-1529 (``None`` stands for ``usize::MAX``); the rule itself lives behind the C ABI (szb_match_embedding)."""
+    if not speaker_embeddings:
+        return None
+    ids = np.array(list(speaker_embeddings.keys()), dtype=np.uint64)
+    cents = _f32(np.stack([np.asarray(v, np.float32) for v in speaker_embeddings.values()]))
+    e = _f32(emb)
+    best, sim = C.c_uint64(), C.c_float()
+    N.check(N.lib.szb_match_embedding(N.ptr(e), N.ptr(cents), N.ptr(ids), len(ids), cents.shape[1], float(threshold), C.byref(best),
+                                      C.byref(sim)))
+    return None if best.value == 2 ** 64 - 1 else int(best.value)
 
 
 def _cosine_decision(emb, speaker_embeds, threshold: float) -> Optional[int]:

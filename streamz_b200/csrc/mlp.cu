@@ -1289,6 +1289,24 @@ float szb_cosine_similarity(const float* a, const float* b, uint32_t n) {   // l
     return (na == 0.f || nb == 0.f) ? 0.f : dot / (na * nb);
 }
 
+// identify_speaker_from_embedding (lib.rs:1503-1529): the centroid with the largest cosine similarity wins if it clears the
+// threshold, which is relaxed to 0.7 x threshold while fewer than 20 speakers are known.  The reference walks a HashMap
+// (unspecified order, strict '>'): ties go to whichever entry comes first; here to the first in the caller's order.
+szb_status szb_match_embedding(const float* emb, const float* centroids, const uint64_t* ids, uint32_t n, uint32_t dim, float threshold,
+                               uint64_t* best_id, float* best_sim) {
+    SZB_REQUIRE(best_id && (n == 0 || (emb && centroids)), "szb_match_embedding: NULL argument");
+    float bs = -3.402823466e+38f;                           // f32::MIN
+    uint64_t bi = UINT64_MAX;                               // usize::MAX
+    for (uint32_t i = 0; i < n; ++i) {
+        const float sim = szb_cosine_similarity(emb, centroids + size_t(i) * dim, dim);
+        if (sim > bs) { bs = sim; bi = ids ? ids[i] : i; }
+    }
+    const float dynamic_threshold = n < 20 ? threshold * 0.7f : threshold;
+    *best_id = bs > dynamic_threshold ? bi : UINT64_MAX;
+    if (best_sim) *best_sim = bs;
+    return SZB_OK;
+}
+
 // ---- aggregation ----------------------------------------------------------------------------------------------------
 static szb_status identify_dev(szb_net* net, const float* d_feats, uint64_t n, float threshold, uint64_t* counts, float* sums) {
     szb_ctx* ctx = net->ctx;

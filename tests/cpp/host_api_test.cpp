@@ -71,11 +71,24 @@ int main() {
     REQUIRE(identify_speaker(net, tone_clip(1, 0.7), ex) == 1);
     REQUIRE(identify_speaker_with_threshold(net, tone_clip(0, 0.7), 0.5f, ex).value_or(99) == 0);
     REQUIRE(!identify_speaker_with_threshold(net, tone_clip(0, 0.7), 1.5f, ex).has_value());
-    // --- save / load round trip (lib.rs:1081-1282) ---
+    // --- raw-audio training loops (lib.rs:348-397, 668-732): augment -> extract -> train per epoch, lr * 0.99^step ---
+    {
+        SimpleNeuralNet raw(FEATURE_SIZE, 512, 256, 2, 4);
+        const float first = pretrain_network(raw, tone_clip(0, 0.6), 0, 2, 1, 0.01f, DEFAULT_DROPOUT, 8, 21);
+        REQUIRE(std::isfinite(first) && first > 0.f);
+        REQUIRE(pretrain_network(raw, std::vector<int16_t>(500), 0, 2, 3, 0.01f, DEFAULT_DROPOUT, 8, 21) == 0.0f);   // lib.rs:392-396
+        std::vector<TrainingClip> clips = { { "a.wav", tone_clip(0, 0.5), 0 }, { "b.wav", tone_clip(1, 0.5), 1 } };
+        float lf = 0.f;
+        for (int round = 0; round < 6; ++round) lf = train_from_files(raw, clips, 2, 1, 0.01f, DEFAULT_DROPOUT, 8, 30 + round);
+        REQUIRE(std::isfinite(lf) && lf < first);
+    }
+    // --- save / load round trip (lib.rs:1081-1282), with the speaker embeddings the CLI stores before saving (main.rs:845-856) ---
     const char* path = "/tmp/streamz_b200_cpp_model.npz";
+    net.set_embeddings({ { std::vector<float>(256, 0.5f), 0.9f, 0.01f }, { std::vector<float>(256, -0.25f), 0.8f, 0.02f } });
     net.save(path);
     SimpleNeuralNet back = SimpleNeuralNet::load(path);
     REQUIRE(back.output_size() == 2);
+    REQUIRE(back.embeddings().size() == 2 && std::get<0>(back.embeddings()[1])[7] == -0.25f && std::get<1>(back.embeddings()[0]) == 0.9f);
     const auto p0 = net.forward(fmap.begin()->second[3]), p1 = back.forward(fmap.begin()->second[3]);
     REQUIRE(p0[0] == p1[0] && p0[1] == p1[1]);
     net.add_output_class();
