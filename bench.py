@@ -232,6 +232,30 @@ def cpu_baseline_block(cores, seconds, cap):
     return out
 
 
+def pin_to_gpu_numa_node(torch, local):
+    """Multi-rank runs share one host: bind this rank's threads to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI
+    function) BEFORE the pinned staging buffers are allocated, so they are first-touched on the GPU's own NUMA node and the
+    host-buffer e2e path of every rank copies through its local memory controller and PCIe root.  Returns a short description
+    for the JSON line, or None when the topology cannot be read."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0"
+        cpus = open(os.path.join(path, "local_cpulist")).read().strip()
+        node = open(os.path.join(path, "numa_node")).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": int(node), "cpus": cpus, "bound": bool(ids)}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
     """configs[2]: one epoch over 1 M cached windows per GPU, 100 speakers, batch 4096 per GPU, lr 0.01, dropout 0.2.
     At N > 1 the epoch is timed with BOTH gradient exchanges (overlapped NCCL all-reduces; the two-shot peer-memory exchange
@@ -411,6 +435,7 @@ def main():
         raise SystemExit("bench.py needs a B200: streamz_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -529,7 +554,7 @@ def main():
                    "clips_per_gpu": n_clips, "windows_per_gpu": total, "audio_seconds_per_step": world * audio_s,
                    "l2": "inputs (3.2 GB) and outputs (2.6 GB) per step exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(n_clips * n_in * 2), "d2h_bytes_per_step": int(total * 240),
-                "steps": e2e_steps, "checksum": checksum},
+                "steps": e2e_steps, "checksum": checksum, "per_gpu": e2e_value / world, "host_binding_rank0": numa},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "kernel": "extract_kernel", "launch_ms": k_avg_ms, "launches_timed": int(k_n),

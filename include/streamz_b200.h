@@ -61,6 +61,12 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out);
 void szb_ctx_destroy(szb_ctx* ctx);
 szb_status szb_ctx_sync(szb_ctx* ctx);
 int32_t szb_ctx_sm_count(const szb_ctx* ctx);
+/* szb_extract_batch(_dev) with rate != 44100: enable = 1 runs the polyphase FIR inside the extraction kernel's staging -- every
+ * 33-hop tile of the 44.1 kHz signal is produced in shared memory from the original-rate clip and never written to HBM; enable = 0
+ * (the DEFAULT) runs resample_kernel -> extract_kernel with the 44.1 kHz i16 intermediate in HBM.  Identical results (bit for
+ * bit, tested); the fused kernel moves 4x less DRAM traffic but measured 45 % slower on B200, hence the default.
+ * Falls back to the two-kernel path for rates above 44.1 kHz or clips that do not start on 16-byte boundaries. */
+szb_status szb_ctx_set_fused_resample(szb_ctx* ctx, int32_t enable);
 /* OPTIONAL mode of the device-resident szb_extract_batch_dev with rate != 44100: the batch is processed in chunks whose
  * 44.1 kHz intermediate (chunk_mb MB) is written by the resampler into a two-slot ring that stays in the 126 MB L2 and is
  * read back by the extraction kernel from there, so it never makes the round trip through HBM.  streams = 2 runs the
@@ -229,6 +235,12 @@ szb_status szb_identify_counts(szb_net* net, const float* feats, uint64_t n_wind
                                uint64_t* counts /* [n_out] */);
 szb_status szb_identify_counts_dev(szb_net* net, const float* d_feats, uint64_t n_windows, float threshold,
                                    uint64_t* counts /* host [n_out] */);
+/* Batched form for many clips (the identification loop of a whole shard, BASELINE configs[3]): windows of clip c are rows
+ * [win_off[c], win_off[c+1]) of d_feats -- the layout szb_extract_batch_dev leaves -- and counts[c][k] is the histogram of
+ * lib.rs:1389-1402 for clip c.  One pass of large forward batches with a per-window clip lookup instead of one launch
+ * sequence and one synchronising read-back per clip.  counts: HOST [n_clips][n_out] u32; win_off: host, n_clips + 1. */
+szb_status szb_identify_counts_batch_dev(szb_net* net, const float* d_feats, const uint64_t* win_off, uint32_t n_clips,
+                                         float threshold, uint32_t* counts);
 /* Per-class sum of window probabilities (lib.rs:1290-1297, 1319-1328). */
 szb_status szb_identify_sums(szb_net* net, const float* feats, uint64_t n_windows, float* sums /* [n_out] */);
 /* identify_speaker_list (lib.rs:1383-1411): extraction + forward + histogram + stable sort by count descending. */

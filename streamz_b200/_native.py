@@ -43,6 +43,7 @@ SIGNATURES = {
     "szb_ctx_destroy": (None, [vp]),
     "szb_ctx_sync": (i32, [vp]),
     "szb_ctx_sm_count": (i32, [vp]),
+    "szb_ctx_set_fused_resample": (i32, [vp, i32]),
     "szb_ctx_set_l2_ring": (i32, [vp, i32, i32]),
     "szb_ctx_launch_count": (u64, [vp]),
     "szb_timer_start": (i32, [vp]),
@@ -96,6 +97,7 @@ SIGNATURES = {
     "szb_net_train_from_files": (i32, [vp, vp, vp, vp, u32, u32, f32, f32, u32, u64, P(f64), P(u64)]),
     "szb_identify_counts": (i32, [vp, vp, u64, f32, vp]),
     "szb_identify_counts_dev": (i32, [vp, vp, u64, f32, vp]),
+    "szb_identify_counts_batch_dev": (i32, [vp, vp, vp, u32, f32, vp]),
     "szb_identify_sums": (i32, [vp, vp, u64, vp]),
     "szb_identify_speaker_list": (i32, [vp, vp, u64, f32, vp, u32, P(u32)]),
     "szb_net_embedding_size": (i32, [vp, P(u32)]),

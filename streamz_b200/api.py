@@ -559,6 +559,27 @@ def identify_counts(net: SimpleNeuralNet, windows, threshold: float) -> np.ndarr
     return counts.astype(np.int64)
 
 
+def identify_counts_batch(net: SimpleNeuralNet, windows_per_clip: Sequence[np.ndarray], threshold: float) -> np.ndarray:
+    """The histograms of identify_speaker_list (lib.rs:1389-1402) for many clips in one call: ``counts[c]`` equals
+    ``identify_counts(net, windows_per_clip[c], threshold)``.  (szb_identify_counts_batch_dev: large forward batches over the
+    concatenated windows with a per-window clip lookup.)"""
+    n_in = net.dims[0]
+    wins = [_f32(w).reshape(-1, n_in) for w in windows_per_clip]
+    off = np.concatenate([[0], np.cumsum([len(w) for w in wins])]).astype(np.uint64)
+    counts = np.zeros((len(wins), net.output_size()), dtype=np.uint32)
+    if not wins:
+        return counts
+    flat = _f32(np.concatenate(wins)) if int(off[-1]) else np.zeros((0, n_in), np.float32)
+    d = net.ctx.dev_alloc(max(1, flat.nbytes))
+    try:
+        if flat.nbytes:
+            net.ctx.h2d(d, flat)
+        N.check(N.lib.szb_identify_counts_batch_dev(net._h, C.c_void_p(d), N.ptr(off), len(wins), float(threshold), N.ptr(counts)))
+    finally:
+        net.ctx.dev_free(d)
+    return counts
+
+
 def identify_sums(net: SimpleNeuralNet, windows) -> np.ndarray:
     w = _f32(windows).reshape(-1, net.dims[0])
     sums = np.zeros(net.output_size(), dtype=np.float32)

@@ -153,6 +153,7 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
     if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_CHUNK_MB")) ctx->l2_chunk_mb = std::max(0, atoi(e));
+    if (const char* e = getenv("SZB_FUSED_RESAMPLE")) ctx->fuse_resample = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_STREAMS")) ctx->l2_streams = atoi(e) > 1 ? 2 : 1;
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
@@ -208,6 +209,12 @@ szb_status szb_ctx_sync(szb_ctx* ctx) {
     return SZB_OK;
 }
 int32_t szb_ctx_sm_count(const szb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+szb_status szb_ctx_set_fused_resample(szb_ctx* ctx, int32_t enable) {
+    SZB_REQUIRE(ctx, "szb_ctx_set_fused_resample: ctx is NULL");
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->fuse_resample = enable != 0;
+    return SZB_OK;
+}
 szb_status szb_ctx_set_l2_ring(szb_ctx* ctx, int32_t chunk_mb, int32_t streams) {
     SZB_REQUIRE(ctx && chunk_mb >= 0 && (streams == 1 || streams == 2), "szb_ctx_set_l2_ring: chunk_mb >= 0, streams 1 or 2");
     SZB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -451,8 +458,13 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     // leaves the 126 MB L2 -- the extraction kernel of the chunk reads it back from L2 and the slot is overwritten two chunks
     // later, still dirty in cache, so the 2 x 8.8 GB round trip through HBM of the unchunked pipeline disappears (ncu DRAM
     // bytes: profiles/).  Device-resident call at 44.1 kHz: one chunk.
+    // fused mode: no resampler launch at all -- the extraction kernel filters every 33-hop tile from the original-rate clip in
+    // shared memory (frontend.cu).  Needs 16-byte aligned clip starts (cp.async) and a supported rate.
+    bool fused = resample && ctx->fuse_resample && fused_resample_supported(rate) && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0;
+    for (uint32_t c = 0; c < n_clips && fused; ++c)
+        if (woff[c + 1] > woff[c] && (((clip_off[c] - first) & 7) != 0 || woff[c + 1] - woff[c] > 10000000ull)) fused = false;
     const uint64_t l2_chunk_bytes = uint64_t(ctx->l2_chunk_mb) << 20;
-    const bool ring = resample && !piped && l2_chunk_bytes > 0;
+    const bool ring = resample && !fused && !piped && l2_chunk_bytes > 0;
     std::vector<uint32_t> chunk_begin{ 0 };
     if (ring) {
         uint64_t acc = 0;
@@ -482,7 +494,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     uint64_t* d_in_off = nullptr;
     uint64_t* d_out_off = nullptr;
     std::vector<uint64_t> off_ring;   // ring mode: clip c's 44.1 kHz samples start at misc[off_ring[c]] (slot = chunk & 1)
-    if (resample) {                   // ... or at misc[off44[c]] after the resampler
+    if (resample && !fused) {         // ... or at misc[off44[c]] after the resampler
         if (ring) {
             uint64_t slot = 0;
             for (size_t k = 0; k + 1 < chunk_begin.size(); ++k) slot = std::max(slot, off44[chunk_begin[k + 1]] - off44[chunk_begin[k]]);
@@ -513,10 +525,15 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
     std::vector<Segment> segs;
     std::vector<size_t> seg_begin(n_chunks + 1, 0);
     std::vector<uint64_t> seg_off(size_t(n_clips) + 1);
-    for (uint32_t c = 0; c <= n_clips; ++c) seg_off[c] = resample ? (ring ? off_ring[c] : off44[c]) : clip_off[c] - first;
+    for (uint32_t c = 0; c <= n_clips; ++c) seg_off[c] = (resample && !fused) ? (ring ? off_ring[c] : off44[c]) : clip_off[c] - first;
+    std::vector<uint64_t> n_in_of;
+    if (fused) {
+        n_in_of.resize(n_clips);
+        for (uint32_t c = 0; c < n_clips; ++c) n_in_of[c] = clip_off[c + 1] - clip_off[c];
+    }
     for (size_t k = 0; k < n_chunks; ++k) {
         seg_begin[k] = segs.size();
-        build_segments(seg_off.data(), woff.data(), chunk_begin[k], chunk_begin[k + 1], ctx->sm_count, segs);
+        build_segments(seg_off.data(), woff.data(), chunk_begin[k], chunk_begin[k + 1], ctx->sm_count, segs, fused ? n_in_of.data() : nullptr);
     }
     seg_begin[n_chunks] = segs.size();
     SZB_TRY(upload_segments(ctx, segs, uint32_t(n_chunks)));
@@ -547,7 +564,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
             SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k], ctx->copy_in));
             SZB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
         }
-        if (resample) {
+        if (resample && !fused) {
             uint64_t max_out = 0;
             for (uint32_t c = c0; c < c1; ++c) max_out = std::max(max_out, szb_resample_out_len(clip_off[c + 1] - clip_off[c], rate));
             if (ring && ctx->l2_streams > 1) {
@@ -570,7 +587,7 @@ static szb_status extract_batch_impl(szb_ctx* ctx, const int16_t* d_pcm, const i
                 SZB_TRY(launch_resample(ctx, d_pcm, d_in_off + c0, d_out_off + c0, c1 - c0, max_out, rate, ctx->misc.as<int16_t>()));
             }
         }
-        SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats, aligned16));
+        SZB_TRY(launch_extract(ctx, d_pcm44, seg_begin[k], seg_begin[k + 1] - seg_begin[k], uint32_t(k), d_feats, aligned16, fused ? rate : 0u));
         if (ring && ctx->l2_streams > 1) SZB_CUDA(cudaEventRecord(ctx->ring_ev[2 + (k & 1)], ctx->stream));
         if (piped) {
             SZB_CUDA(cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));

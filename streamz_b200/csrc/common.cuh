@@ -94,6 +94,11 @@ struct szb_ctx {
     // (capi.cu).  Off by default -- measured on B200 (profiles/r02_l2_ring_sweep.txt): every setting is slower than the
     // single-chunk pipeline (21.7 ms per configs[1] step): 29.6 ms at 96 MB chunks, 37.8 ms at 32 MB; relaunching the
     // persistent extraction kernel per chunk costs more than the HBM round trip it saves (neither kernel is HBM-bound).
+    // szb_ctx_set_fused_resample / SZB_FUSED_RESAMPLE=1: FIR inside the extraction kernel's staging (no 44.1 kHz intermediate
+    // in HBM).  Bit-identical, but measured SLOWER on B200 (31.5 ms against 21.7 ms per configs[1] step: the FIR's 51 tap
+    // registers do not fit beside the extraction kernel's state at 96 registers per thread, and its phases serialise behind
+    // block barriers instead of overlapping across four independent CTAs), so it is off by default.
+    bool fuse_resample = false;
     int l2_chunk_mb = 0;                                 // SZB_L2_CHUNK_MB (0 = one chunk, intermediate through HBM)
     int l2_streams = 2;                                  // SZB_L2_STREAMS: resampler of chunk k + 1 under the tail of extract k
     cudaEvent_t ring_ev[5] = {};                         // [0,1] resample done, [2,3] extract done (per slot), [4] tables uploaded

@@ -74,10 +74,31 @@ __device__ __forceinline__ void s16x2_to_f32(uint32_t v, float& lo, float& hi) {
     hi = __uint_as_float(h) - 8421376.f;
 }
 
-template <bool kAligned16>   // every segment's first sample is 16-byte aligned: 128-bit loads, no scalar fallback code
+// clamp to [-32768, 32767] and truncate toward zero (lib.rs:205-208) in ONE conversion: a float -> s16 cvt saturates at the
+// ends of the destination range (two FMNMX fewer per output sample than clamping in float first; same bits)
+__device__ __forceinline__ int16_t f32_to_s16_sat_rz(float v) {
+    short r;
+    asm("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return r;
+}
+
+// Fused mode (kFusedD > 0): `pcm` holds the clips at their ORIGINAL rate and the polyphase FIR of resample_kernel runs inside the
+// staging of every tile, so the 44.1 kHz signal exists only as the 33-hop tile in shared memory (same taps, same FMA order,
+// same saturating conversion: the tile is bit-identical to what resample_kernel would have written to HBM).  Threads are
+// dealt to output rows of Lb samples in teams of `wpt` warps exactly as resample_kernel deals them to a CTA (K = 3 adjacent
+// outputs per thread, `lpw` lanes per warp so a window load is one shared-memory wavefront).
+struct FusedParams {
+    const float* taps;       // [L][16] polyphase taps of the rate
+    uint32_t L, M;           // 44100 / rate reduced
+    uint32_t Lb, G;          // outputs per row (multiple of lcm(L, 3)), column threads per row
+    uint32_t in_per_row;     // Lb * M / L
+    uint32_t lpw, wpt, n_teams;
+};
+
+template <bool kAligned16, int kFusedD = 0>   // aligned: every segment's first sample is 16-byte aligned (128-bit loads)
 __global__ void __launch_bounds__(kThreads, 1)
 extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs, uint32_t n_segs,
-               unsigned int* __restrict__ queue, float* __restrict__ out) {
+               unsigned int* __restrict__ queue, float* __restrict__ out, const FusedParams fp = FusedParams{}) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_pcm = reinterpret_cast<uint32_t*>(smem + kOffPcm);
     cpx* s_S = reinterpret_cast<cpx*>(smem + kOffS);          // one 64-bit (re, im) pair per element
@@ -96,7 +117,24 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
     for (int i = tid; i < kMelPad * kTile; i += kThreads) s_P[kBins * kTile + i] = 0.f;   // rows 401.. stay zero
     for (int i = tid; i < kMelWCap; i += kThreads) s_melw[i] = c_melw[i];
     __syncthreads();
-
+    // fused mode: the thread's place in the resampler's row walk never changes; its three phases (< 4096 each), their window
+    // shifts (2 bits each) and its window start are packed into two registers that stay live across the whole kernel
+    uint32_t f_pk0 = 0, f_pk1 = 0;
+    if (kFusedD > 0) {
+        const uint32_t team = uint32_t(warp) / fp.wpt, wl = uint32_t(warp) - team * fp.wpt, g = wl * fp.lpw + uint32_t(lane);
+        if (team < fp.n_teams && g < fp.G && (uint32_t(lane) < fp.lpw || wl == fp.wpt - 1)) {
+            const uint32_t q0 = uint32_t((uint64_t(3 * g) * fp.M) / fp.L);
+            uint32_t p[3], d[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint64_t pos = uint64_t(3 * g + k) * fp.M;
+                d[k] = uint32_t(pos / fp.L) - q0;
+                p[k] = uint32_t(pos % fp.L);
+            }
+            f_pk0 = p[0] | (p[1] << 12) | ((d[0] | (d[1] << 2) | (d[2] << 4)) << 24);
+            f_pk1 = p[2] | (q0 << 12) | 0x80000000u;      // bit 31: this thread filters
+        }
+    }
     for (;;) {
         if (tid == 0) s_seg = atomicAdd(queue, 1u);
         __syncthreads();
@@ -122,12 +160,12 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
         constexpr int kVecPerHop = kHop / 8;                       // 50 uint4 per hop
         constexpr int kVecPerTile = kPcmRows * kVecPerHop;         // 1650
         constexpr int kPre = (kVecPerTile + kThreads - 1) / kThreads;  // 3
-        uint4 pre[kPre];
+        uint4 pre[kFusedD == 0 ? kPre : 1];
         auto fetch_tile = [&](uint32_t ta) {
             const uint32_t tnf = min(uint32_t(kTile), f_hi - ta);
             const int16_t* src = clip + size_t(ta) * kHop;
 #pragma unroll
-            for (int r = 0; r < kPre; ++r) {
+            for (int r = 0; r < (kFusedD == 0 ? kPre : 0); ++r) {
                 const int q = tid + r * kThreads;
                 pre[r] = make_uint4(0u, 0u, 0u, 0u);
                 if (q < int(tnf + 1) * kVecPerHop) {
@@ -144,18 +182,117 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 }
             }
         };
-        fetch_tile(f_lo);
+        // ---- fused mode: the tile's span of the ORIGINAL-rate clip is requested with cp.async one tile ahead (the staging buffer is
+        //      its landing zone), expanded to float into the (idle) FFT buffer, and filtered into the staging buffer.
+        constexpr int kFW = kResTaps + (kFusedD > 0 ? kFusedD : 1);     // window of one thread: 16 taps + the spread of its 3 outputs
+        int16_t* s_raw = reinterpret_cast<int16_t*>(s_pcm);
+        float* s_in = reinterpret_cast<float*>(s_S);
+        const int64_t n_in = int64_t(sg.pad);                          // input samples of the clip (fused mode)
+        auto tile_rows = [&](uint32_t ta, uint32_t& R_lo, uint32_t& n_rows) {   // output rows of Lb samples that cover the tile's hops
+            const uint32_t tnf = min(uint32_t(kTile), f_hi - ta);
+            const uint32_t J0 = ta * uint32_t(kHop), J1 = (ta + tnf + 1) * uint32_t(kHop);   // < 2^32: the host admits clips below 10 M windows
+            R_lo = J0 / fp.Lb;                                                     // (32-bit: a 64-bit division costs ~30 instructions
+            n_rows = (J1 - 1) / fp.Lb - R_lo + 1;                                  //  per thread and tile)
+        };
+        auto issue_raw = [&](uint32_t ta) {
+            uint32_t R_lo, n_rows;
+            tile_rows(ta, R_lo, n_rows);
+            const int64_t i_lo = int64_t(R_lo) * fp.in_per_row - (kResTaps / 2 - 1), a0 = i_lo & ~int64_t(7);
+            const uint32_t n_chunks = (uint32_t(i_lo - a0) + n_rows * fp.in_per_row + kFW + 7) / 8;
+            for (uint32_t c = tid; c < n_chunks; c += kThreads) {
+                const int64_t gs = a0 + 8 * int64_t(c);
+                const bool in = gs >= 0 && gs < n_in;
+                const uint32_t bytes = in ? uint32_t(min(int64_t(16), (n_in - gs) * 2)) : 0u;   // the copy zero-fills the rest
+                const uint32_t dst = uint32_t(__cvta_generic_to_shared(s_raw + 8 * c));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(in ? clip + gs : clip), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (kFusedD == 0) fetch_tile(f_lo); else issue_raw(f_lo);
 
         for (uint32_t a = f_lo; a < f_hi; a += kTile) {
             const uint32_t nf = min(uint32_t(kTile), f_hi - a);
+            if (kFusedD == 0) {
             // ---- 1. prefetched registers -> staging buffer (row stride 201 words keeps lane = frame conflict-free) ----
 #pragma unroll
-            for (int r = 0; r < kPre; ++r) {
+            for (int r = 0; r < (kFusedD == 0 ? kPre : 0); ++r) {
                 const int q = tid + r * kThreads;
                 if (q < kVecPerTile) {
                     const int h = q / kVecPerHop, c4 = q - h * kVecPerHop;
                     uint32_t* d = s_pcm + h * kHopStride + c4 * 4;
                     d[0] = pre[r].x; d[1] = pre[r].y; d[2] = pre[r].z; d[3] = pre[r].w;
+                }
+            }
+            } else {
+            // ---- 1f. raw span -> float -> polyphase FIR -> 44.1 kHz tile (resample_to_44100, lib.rs:186-209, in shared memory) ----
+                uint32_t R_lo, n_rows;
+                tile_rows(a, R_lo, n_rows);
+                const int64_t i_lo = int64_t(R_lo) * fp.in_per_row - (kResTaps / 2 - 1), a0 = i_lo & ~int64_t(7);
+                const uint32_t in_shift = uint32_t(i_lo - a0);
+                const uint32_t n_chunks = (in_shift + n_rows * fp.in_per_row + kFW + 7) / 8;
+                // this thread's taps: its three phases' rows, shifted by exact zeros to the common window start (registers are
+                // reloaded per tile: they cannot stay live across the FFT stages)
+                const uint32_t team = uint32_t(warp) / fp.wpt, g = (uint32_t(warp) - team * fp.wpt) * fp.lpw + uint32_t(lane);
+                const uint32_t q0 = (f_pk1 >> 12) & 0x7FFFFu;
+                const bool worker = (f_pk1 >> 31) != 0;
+                const uint32_t f_p[3] = { f_pk0 & 0xFFFu, (f_pk0 >> 12) & 0xFFFu, f_pk1 & 0xFFFu };
+                const uint32_t f_d[3] = { (f_pk0 >> 24) & 3u, (f_pk0 >> 26) & 3u, (f_pk0 >> 28) & 3u };
+                float c[3][kFW];
+                if (worker) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4* cp4 = reinterpret_cast<const float4*>(fp.taps + size_t(f_p[k]) * kResTaps);
+                        float row[kResTaps];
+#pragma unroll
+                        for (int v = 0; v < kResTaps / 4; ++v) {
+                            const float4 t4 = __ldg(cp4 + v);
+                            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+                        }
+#pragma unroll
+                        for (int t = 0; t < kFW; ++t) {
+                            float v = 0.f;
+#pragma unroll
+                            for (int dd = 0; dd <= (kFusedD > 0 ? kFusedD : 1); ++dd)
+                                if (t - dd >= 0 && t - dd < kResTaps && f_d[k] == uint32_t(dd)) v = row[t - dd];
+                            c[k][t] = v;
+                        }
+                    }
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+                for (uint32_t cidx = tid; cidx < n_chunks; cidx += kThreads) {
+                    const uint4 rawv = *reinterpret_cast<const uint4*>(s_raw + 8 * cidx);
+                    float4 lo, hi;
+                    s16x2_to_f32(rawv.x, lo.x, lo.y); s16x2_to_f32(rawv.y, lo.z, lo.w);
+                    s16x2_to_f32(rawv.z, hi.x, hi.y); s16x2_to_f32(rawv.w, hi.z, hi.w);
+                    reinterpret_cast<float4*>(s_in)[2 * cidx] = lo;
+                    reinterpret_cast<float4*>(s_in)[2 * cidx + 1] = hi;
+                }
+                __syncthreads();                                   // float span complete; the raw span may be overwritten
+                if (worker) {
+                    const uint32_t J0 = a * uint32_t(kHop);
+                    const int32_t span_out = int32_t(nf + 1) * kHop;
+                    for (uint32_t r = team; r < n_rows; r += fp.n_teams) {
+                        const float* wv = s_in + in_shift + r * fp.in_per_row + q0;
+                        float w[kFW];
+#pragma unroll
+                        for (int t = 0; t < kFW; ++t) w[t] = wv[t];
+                        float acc[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+                        for (int t = 0; t < kFW; ++t) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) acc[k] = fmaf(c[k][t], w[t], acc[k]);
+                        }
+                        const int32_t jj0 = int32_t((R_lo + r) * fp.Lb + 3 * g) - int32_t(J0);    // position inside the tile's 33 hops
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int32_t jj = jj0 + k;
+                            if (jj >= 0 && jj < span_out) {
+                                const int32_t h = (jj * 5243) >> 21;                           // jj / 400 for jj < 16384
+                                reinterpret_cast<int16_t*>(s_pcm)[jj + 2 * h] = f32_to_s16_sat_rz(acc[k]);   // hop rows are 402 halfwords apart
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -184,7 +321,9 @@ extract_kernel(const int16_t* __restrict__ pcm, const Segment* __restrict__ segs
                 }
             }
             __syncthreads();
-            if (a + kTile < f_hi) fetch_tile(a + kTile);   // staging buffer is free again: start the next tile's loads
+            if (a + kTile < f_hi) {                         // staging buffer is free again: start the next tile's loads
+                if (kFusedD == 0) fetch_tile(a + kTile); else issue_raw(a + kTile);
+            }
 
             // ---- 3. stage B: warp = k2, lane = frame.  20-point DFT over n1, in place: row k2*20 + k1 = Z[k2 + 20 k1] --
             {
@@ -386,14 +525,6 @@ __device__ __forceinline__ void res_issue(const int16_t* x, int64_t n_in, int64_
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(in ? x + gs : x), "r"(bytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// clamp to [-32768, 32767] and truncate toward zero (lib.rs:205-208) in ONE conversion: a float -> s16 cvt saturates at the
-// ends of the destination range (two FMNMX fewer per output sample than clamping in float first; same bits)
-__device__ __forceinline__ int16_t f32_to_s16_sat_rz(float v) {
-    short r;
-    asm("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(v));
-    return r;
 }
 
 template <int K, int D>   // K adjacent outputs per thread, whose windows start at most D input samples apart
@@ -618,13 +749,15 @@ szb_status upload_frontend_tables() {
     }
     SZB_CUDA(cudaFuncSetAttribute(extract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
     SZB_CUDA(cudaFuncSetAttribute(extract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
+    SZB_CUDA(cudaFuncSetAttribute(extract_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
+    SZB_CUDA(cudaFuncSetAttribute(extract_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTotal)));
     return SZB_OK;
 }
 
 // Split clips into (clip, window-range) segments: whole clips when there is enough work to fill the machine, else
 // ranges of >= 64 windows so short batches still spread over the SMs.
 void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_t clip_begin, uint32_t clip_end, int sm_count,
-                    std::vector<Segment>& segs) {
+                    std::vector<Segment>& segs, const uint64_t* clip_n_in) {
     const uint64_t total = win_off[clip_end] - win_off[clip_begin];
     uint64_t target = total / (uint64_t(sm_count) * 4);
     target = std::max<uint64_t>(64, std::min<uint64_t>(target, 4096));
@@ -641,6 +774,7 @@ void build_segments(const uint64_t* clip_off44, const uint64_t* win_off, uint32_
             s.n_total = uint32_t(n);
             s.w_begin = uint32_t(n * p / np);
             s.w_end = uint32_t(n * (p + 1) / np);
+            s.pad = clip_n_in ? uint32_t(clip_n_in[c]) : 0u;
             if (s.w_end > s.w_begin) segs.push_back(s);
         }
     }
@@ -662,23 +796,78 @@ szb_status upload_segments(szb_ctx* ctx, const std::vector<Segment>& segs, uint3
     return SZB_OK;
 }
 
+// Geometry of the resampler's row walk for `rate` (shared by resample_kernel's launch and the fused extraction kernel).
+struct ResGeom { uint32_t L, M, Lb, G, D, threads, lpw, in_per_row; };
+static bool res_geometry(uint32_t rate, ResGeom& q) {
+    constexpr uint32_t K = 3;
+    resample_ratio(rate, q.L, q.M);
+    const uint32_t span = uint32_t((uint64_t(K - 1) * q.M + q.L - 1) / q.L);   // K adjacent outputs span at most this many inputs
+    if (span > 5 || q.L > 4096) return false;
+    const uint32_t Lp = q.L / std::gcd(q.L, K) * K;                            // lcm(L, K)
+    const uint32_t mult = std::max<uint32_t>(1, K * 128 / Lp);
+    q.Lb = Lp * mult;
+    q.G = q.Lb / K;
+    if (q.G > 160) return false;
+    q.threads = (q.G + 31) / 32 * 32;
+    q.D = std::max<uint32_t>(1, span);
+    q.in_per_row = uint32_t(uint64_t(q.Lb) * q.M / q.L);
+    // lanes per warp: the most whose K * lpw outputs read at most 32 consecutive input samples, if the row still fits
+    q.lpw = uint32_t((32ull * q.L) / (uint64_t(K) * q.M));
+    const uint32_t n_warps = q.threads / 32;
+    if (q.lpw >= 32 || q.lpw < 24 || (n_warps - 1) * q.lpw + 32 < q.G) q.lpw = 32;
+    return true;
+}
+
+// Can szb_extract_batch(rate != 44100) run the FIR inside the extraction kernel's staging?  (window spread of a thread's three
+// outputs <= 2 samples, i.e. rates up to 44.1 kHz; the tile's raw span fits the staging buffer and its float copy the FFT buffer)
+bool fused_resample_supported(uint32_t rate) {
+    ResGeom q;
+    if (rate == SZB_SAMPLE_RATE || !res_geometry(rate, q) || q.D > 2) return false;
+    const uint64_t rows = (uint64_t(kPcmRows) * kHop + q.Lb - 1) / q.Lb + 1;   // output rows a 33-hop tile can touch
+    const uint64_t span = rows * q.in_per_row + kResTaps + q.D + 8;            // input samples staged per tile
+    return span * 2 + 32 <= kSmemPcm && span * 4 + 64 <= kSmemS && kWarps / (q.threads / 32) >= 1;
+}
+
 // Launches the extraction kernel over segments [seg_begin, seg_begin + n_segs) of the uploaded table, queue `queue`.
+// fused_rate != 0: d_pcm44 holds the clips at `fused_rate` Hz and the kernel resamples each tile itself (segments carry the
+// clips' input offsets and lengths).
 szb_status launch_extract(szb_ctx* ctx, const int16_t* d_pcm44, size_t seg_begin, size_t n_segs, uint32_t queue, float* d_feats,
-                          bool aligned16) {
+                          bool aligned16, uint32_t fused_rate) {
     if (n_segs == 0) return SZB_OK;
     const int grid = int(std::min<size_t>(n_segs, size_t(ctx->sm_count)));
+    FusedParams fp{};
+    ResGeom q{};
+    if (fused_rate) {
+        SZB_REQUIRE(fused_resample_supported(fused_rate) && res_geometry(fused_rate, q) && aligned16, "fused resampling does not support rate %u",
+                    fused_rate);
+        if (ctx->taps_rate != fused_rate) {
+            const auto taps = resample_taps(fused_rate);
+            SZB_TRY(ctx->taps.reserve(taps.size() * sizeof(float)));
+            SZB_CUDA(cudaMemcpyAsync(ctx->taps.ptr, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            SZB_CUDA(cudaStreamSynchronize(ctx->stream));  // taps is a temporary
+            ctx->taps_rate = fused_rate;
+        }
+        fp.taps = ctx->taps.as<float>();
+        fp.L = q.L; fp.M = q.M; fp.Lb = q.Lb; fp.G = q.G; fp.in_per_row = q.in_per_row; fp.lpw = q.lpw;
+        fp.wpt = q.threads / 32;
+        fp.n_teams = uint32_t(kWarps) / fp.wpt;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->ktime_on) {
         SZB_CUDA(cudaEventCreate(&e0));
         SZB_CUDA(cudaEventCreate(&e1));
         SZB_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    if (aligned16)
-        extract_kernel<true><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
-                                                                         ctx->counter.as<unsigned int>() + queue, d_feats);
+    const Segment* sp = ctx->segs.as<Segment>() + seg_begin;
+    unsigned int* qp = ctx->counter.as<unsigned int>() + queue;
+    if (fused_rate && q.D == 1)
+        extract_kernel<true, 1><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, sp, uint32_t(n_segs), qp, d_feats, fp);
+    else if (fused_rate)
+        extract_kernel<true, 2><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, sp, uint32_t(n_segs), qp, d_feats, fp);
+    else if (aligned16)
+        extract_kernel<true><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, sp, uint32_t(n_segs), qp, d_feats);
     else
-        extract_kernel<false><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, ctx->segs.as<Segment>() + seg_begin, uint32_t(n_segs),
-                                                                          ctx->counter.as<unsigned int>() + queue, d_feats);
+        extract_kernel<false><<<grid, kThreads, kSmemTotal, ctx->stream>>>(d_pcm44, sp, uint32_t(n_segs), qp, d_feats);
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (ctx->ktime_on) {
@@ -706,11 +895,10 @@ static szb_status launch_resample_t(szb_ctx* ctx, dim3 grid, uint32_t threads, s
 template <int K>
 static szb_status launch_resample_k(szb_ctx* ctx, const int16_t* d_in, const uint64_t* d_in_off, const uint64_t* d_out_off,
                                     uint32_t n_clips, uint64_t max_out, uint32_t rate, int16_t* d_out) {
-    uint32_t L, M;
-    resample_ratio(rate, L, M);
-    // K adjacent outputs span at most ceil((K - 1) M / L) input samples
-    const uint32_t span = uint32_t((uint64_t(K - 1) * M + L - 1) / L);
-    SZB_REQUIRE(span <= 5 && L <= 4096, "resample: unsupported rate %u (L = %u, M = %u)", rate, L, M);
+    static_assert(K == 3, "res_geometry is written for three outputs per thread");
+    ResGeom q;
+    SZB_REQUIRE(res_geometry(rate, q), "resample: unsupported rate %u", rate);
+    const uint32_t L = q.L, M = q.M, Lb = q.Lb, G = q.G, threads = q.threads, D = q.D;
     if (ctx->taps_rate != rate) {
         const auto taps = resample_taps(rate);
         SZB_TRY(ctx->taps.reserve(taps.size() * sizeof(float)));
@@ -718,14 +906,7 @@ static szb_status launch_resample_k(szb_ctx* ctx, const int16_t* d_in, const uin
         SZB_CUDA(cudaStreamSynchronize(ctx->stream));  // taps is a temporary
         ctx->taps_rate = rate;
     }
-    const uint32_t Lp = L / std::gcd(L, uint32_t(K)) * K;   // lcm(L, K)
-    const uint32_t mult = std::max<uint32_t>(1, K * 128 / Lp);
-    const uint32_t Lb = Lp * mult, G = Lb / K;              // G threads cover one row of Lb outputs
-    SZB_REQUIRE(G <= 160, "resample: rate %u needs %u threads per row", rate, G);
-    const uint32_t threads = (G + 31) / 32 * 32;
-    const uint32_t D = std::max<uint32_t>(1, span);
-    const uint64_t in_per_row = uint64_t(Lb) * M / L;
-    const size_t smem = res_layout(uint32_t(in_per_row), Lb, int(kResTaps + D)).total;
+    const size_t smem = res_layout(q.in_per_row, Lb, int(kResTaps + D)).total;
     SZB_REQUIRE(smem <= 200 * 1024, "resample: rate %u needs %zu bytes of shared memory", rate, smem);
     const uint64_t tiles = ((max_out + Lb - 1) / Lb + kResRows - 1) / kResRows;
     const uint32_t gy = std::min<uint32_t>(n_clips, 65535);

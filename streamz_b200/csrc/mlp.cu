@@ -130,7 +130,9 @@ static szb_status gemm(szb_ctx* ctx, int M, int N, int K, const float* A, int ld
 __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, int mode, float* __restrict__ probs,
                                const uint32_t* __restrict__ labels, const float* __restrict__ target_vec,
                                const uint8_t* __restrict__ valid, float* __restrict__ tail, float threshold,
-                               unsigned long long* __restrict__ hist, float* __restrict__ sums, float* __restrict__ zT, int ldzT) {
+                               unsigned long long* __restrict__ hist, float* __restrict__ sums, float* __restrict__ zT, int ldzT,
+                               const unsigned long long* __restrict__ clip_off = nullptr, uint32_t n_clips = 0,
+                               unsigned long long row_base = 0, uint32_t* __restrict__ clip_hist = nullptr) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -195,7 +197,19 @@ __global__ void softmax_kernel(float* __restrict__ z, int rows, int C, int ldz, 
             const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
             if (ob > best || (ob == best && oc > best_c)) { best = ob; best_c = oc; }
         }
-        if (lane == 0 && best_c >= 0 && best >= threshold) atomicAdd(&hist[best_c], 1ull);  // lib.rs:1398-1400
+        if (lane == 0 && best_c >= 0 && best >= threshold) {                                 // lib.rs:1398-1400
+            if (clip_hist) {     // batched form: the window's clip = last c with clip_off[c] <= global row (empty clips skipped)
+                const unsigned long long g = row_base + uint32_t(row);
+                uint32_t lo = 0, hi = n_clips;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (clip_off[mid] <= g) lo = mid; else hi = mid;
+                }
+                atomicAdd(&clip_hist[size_t(lo) * C + best_c], 1u);
+            } else {
+                atomicAdd(&hist[best_c], 1ull);
+            }
+        }
     }
     if ((mode & 2) && lane == 0 && ok) atomicAdd(&tail[0], 1.f);
 }
@@ -1344,6 +1358,46 @@ szb_status szb_identify_counts(szb_net* net, const float* feats, uint64_t n, flo
         SZB_CUDA(cudaMemcpyAsync(ctx->x.ptr, feats, n * net->n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     return identify_dev(net, ctx->x.as<float>(), n, threshold, counts, nullptr);
+}
+
+szb_status szb_identify_counts_batch_dev(szb_net* net, const float* d_feats, const uint64_t* win_off, uint32_t n_clips, float threshold,
+                                         uint32_t* counts) {
+    SZB_REQUIRE(net && win_off && counts, "szb_identify_counts_batch_dev: NULL argument");
+    if (n_clips == 0) return SZB_OK;
+    for (uint32_t c = 0; c < n_clips; ++c)
+        SZB_REQUIRE(win_off[c + 1] >= win_off[c], "szb_identify_counts_batch_dev: win_off not monotone at %u", c);
+    const uint64_t n = win_off[n_clips] - win_off[0];
+    szb_ctx* ctx = net->ctx;
+    const uint32_t C = net->n_out;
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    const size_t hist_bytes = size_t(n_clips) * C * sizeof(uint32_t), off_bytes = (size_t(n_clips) + 1) * sizeof(uint64_t);
+    SZB_TRY(net->hist.reserve(hist_bytes + off_bytes + 16));
+    uint32_t* d_hist = net->hist.as<uint32_t>();
+    unsigned long long* d_off = reinterpret_cast<unsigned long long*>(net->hist.as<unsigned char>() + ((hist_bytes + 15) & ~size_t(15)));
+    SZB_CUDA(cudaMemsetAsync(d_hist, 0, hist_bytes, ctx->stream));
+    void* hp = nullptr;
+    SZB_TRY(ctx->h_stage.acquire(off_bytes, &hp));
+    std::memcpy(hp, win_off, off_bytes);
+    SZB_CUDA(cudaMemcpyAsync(d_off, hp, off_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
+    if (n > 0) {
+        SZB_REQUIRE(d_feats, "szb_identify_counts_batch_dev: d_feats is NULL");
+        constexpr uint64_t kRows = 1u << 17;             // larger chunks than the per-clip path: few launches over a whole shard
+        SZB_TRY(net_reserve_rows(net, std::min(n, kRows)));
+        for (uint64_t r0 = 0; r0 < n; r0 += kRows) {
+            const int nb = int(std::min(kRows, n - r0));
+            SZB_TRY(forward_rows(net, d_feats + (win_off[0] + r0) * net->n_in, nb));
+            const int wpb = 8;
+            softmax_kernel<<<(nb + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(net->a_z.as<float>(), nb, int(C), int(C), 4, nullptr, nullptr, nullptr,
+                                                                              nullptr, nullptr, threshold, nullptr, nullptr, nullptr, nb, d_off, n_clips,
+                                                                              win_off[0] + r0, d_hist);
+            SZB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+        }
+    }
+    SZB_CUDA(cudaMemcpyAsync(counts, d_hist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SZB_OK;
 }
 
 szb_status szb_identify_sums(szb_net* net, const float* feats, uint64_t n, float* sums) {

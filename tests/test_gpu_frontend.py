@@ -225,3 +225,39 @@ def test_back_to_back_dev_batches_keep_their_own_segment_tables(sz, ctx, oracle,
         want = np.concatenate(want_a if rep % 2 == 0 else want_b)
         assert np.array_equal(got, want), rep
         ctx.dev_free(d_pcm); ctx.dev_free(d_out)
+
+
+def test_fused_resampling_in_the_extraction_kernel_is_bit_identical(sz, ctx, oracle, native):
+    # szb_ctx_set_fused_resample(1): the polyphase FIR runs inside the extraction kernel's staging (no 44.1 kHz intermediate in
+    # HBM).  Rows must equal resample_kernel -> extract_kernel bit for bit, for ragged lengths, clips shorter than a frame after
+    # resampling, several rates, and the unsupported cases must fall back silently (rates above 44.1 kHz; unaligned clip starts).
+    ex = sz.FeatureExtractor(ctx)
+    try:
+        for rate in (16000, 8000, 22050, 32000, 11025, 48000):
+            lens = [int(rate * s) & ~7 for s in (0.31, 1.0, 0.05, 2.37, 0.02)] + [8 * 123]
+            clips = [oracle.synth_clip(i % 3, 70 + i, n / rate + 0.01, rate=rate)[:n] for i, n in enumerate(lens)]
+            native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 0))
+            want = ex.extract_batch(clips, rate=rate)
+            native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 1))
+            got = ex.extract_batch(clips, rate=rate)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert a.shape == b.shape and np.array_equal(a, b), rate
+        odd = [oracle.synth_clip(1, 90, 0.5, rate=16000)[:8003], oracle.synth_clip(2, 91, 0.5, rate=16000)[:7999]]   # 2nd clip starts unaligned
+        native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 0))
+        want = ex.extract_batch(odd, rate=16000)
+        native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 1))
+        got = ex.extract_batch(odd, rate=16000)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        long_clip = [oracle.synth_clip(0, 92, 9.0, rate=16000)]                       # many tiles, several segments
+        assert np.array_equal(ex.extract_batch(long_clip, rate=16000)[0], oracle_free_two_step(sz, ex, native, ctx, long_clip[0]))
+    finally:
+        native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 0))
+
+
+def oracle_free_two_step(sz, ex, native, ctx, clip16):
+    """resample_to_44100 followed by extract through the public API (both on the GPU): the reference of the fused path."""
+    native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 0))
+    out = ex.extract(sz.resample_to_44100(clip16, 16000, ctx))
+    native.check(native.lib.szb_ctx_set_fused_resample(ctx.handle, 1))
+    return out

@@ -294,3 +294,20 @@ def test_npz_and_npy_readers_reject_malformed_files(sz, ctx, native, tmp_path):
     assert npy_status("{'descr' '<f4', 'fortran_order' False, 'shape' (2, 8), }\n") == native.ERR_IO                      # no ':' at all
     assert npy_status("{'descr': '<f4', 'fortran_order':") == native.ERR_IO
     assert npy_status("{'descr': '<f4', 'fortran_order': False, 'shape': (2, 8") == native.ERR_IO
+
+
+def test_batched_identification_equals_per_clip_histograms(sz, ctx, oracle):
+    # szb_identify_counts_batch_dev: one pass over the concatenated windows of many clips, per-window clip lookup;
+    # counts[c] must equal identify_counts of clip c (lib.rs:1389-1402), empty clips included
+    r = np.random.default_rng(21)
+    onet, net = _pair(sz, ctx, oracle, (60, 512, 256, 7), seed=13)
+    sizes = [0, 1, 37, 0, 1101, 5, 64, 0, 300, 0]
+    clips = [r.standard_normal((n, 60)).astype(np.float32) for n in sizes]
+    for thr in (0.0, 0.3, 0.9):
+        got = sz.identify_counts_batch(net, clips, thr)
+        assert got.shape == (len(sizes), 7) and got.dtype == np.uint32
+        for c, w in enumerate(clips):
+            want = sz.identify_counts(net, w, thr) if len(w) else np.zeros(7, np.int64)
+            assert np.array_equal(got[c].astype(np.int64), want), (thr, c)
+        assert np.array_equal(got.astype(np.int64).sum(axis=0), oracle.identify_counts(onet, np.concatenate(clips), thr)) or thr > 0.0
+    assert sz.identify_counts_batch(net, [], 0.5).shape == (0, 7)

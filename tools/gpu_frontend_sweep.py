@@ -21,9 +21,13 @@ torch.cuda.synchronize()
 def step():
     N.check(N.lib.szb_extract_batch_dev(ctx.handle, C.c_void_p(pcm.data_ptr()), N.ptr(off), n_clips, 16000, C.c_void_p(feats.data_ptr()), total, N.ptr(woff)))
 ref = None
-cfgs = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(0, 1), (32, 1), (32, 2)]
+# "fused" = FIR inside the extraction kernel (no intermediate); "mb:streams" = two-kernel path, L2 ring of mb MB (0 = one chunk)
+cfgs = [("fused",) if a == "fused" else tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(0, 1), ("fused",)]
 steps = int(os.environ.get("STEPS", "5"))
-for mb, st in cfgs:
+for cfg in cfgs:
+    fused = cfg[0] == "fused"
+    mb, st = (0, 1) if fused else cfg
+    N.check(N.lib.szb_ctx_set_fused_resample(ctx.handle, 1 if fused else 0))
     N.check(N.lib.szb_ctx_set_l2_ring(ctx.handle, mb, st))
     for _ in range(2):
         step()
@@ -38,4 +42,4 @@ for mb, st in cfgs:
     if ref is None:
         ref = feats.clone()
     same = bool(torch.equal(ref, feats))
-    print(f"chunk {mb:3d} MB streams {st}: {ms:7.3f} ms/step  ({n_clips * 10 / ms / 1e3:.3f} M audio-s/s)  extract kernels {k_ms / steps:7.3f} ms in {k_n // steps} launches/step  identical_to_first={same} checksum {cs:.6f}", flush=True)
+    print(f"{'FUSED (FIR in the extraction kernel)' if fused else f'two kernels, chunk {mb:3d} MB streams {st}'}: {ms:7.3f} ms/step  ({n_clips * 10 / ms / 1e3:.3f} M audio-s/s)  extract kernels {k_ms / steps:7.3f} ms in {k_n // steps} launches/step  identical_to_first={same} checksum {cs:.6f}", flush=True)
