@@ -281,8 +281,8 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
 
     def timed_epoch(exchange):
         if world > 1:
-            active = ctx.comm_peer_exchange(exchange == "peer")
-            if exchange == "peer" and not active:
+            active = ctx.comm_peer_exchange(exchange != "nccl", exchange if exchange != "nccl" else "auto")
+            if exchange != "nccl" and not active:
                 return None
         net = sz.SimpleNeuralNet(60, 512, 256, MLP_SPEAKERS, seed=7, ctx=ctx)   # default arithmetic: 3xTF32 on tcgen05
         def epoch(n_rows):
@@ -316,9 +316,10 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
         runs["none (1 GPU)"] = timed_epoch("none")
     else:
         runs["NCCL all-reduce per layer, overlapped"] = timed_epoch("nccl")
-        r = timed_epoch("peer")
-        if r is not None:
-            runs["two-shot peer-memory exchange fused into the update kernel"] = r
+        for proto in ("two-shot", "one-shot"):
+            r = timed_epoch(proto)
+            if r is not None:
+                runs[f"{proto} peer-memory exchange fused into the update kernel"] = r
         ctx.comm_peer_exchange(False)
     best = min(runs, key=lambda k: runs[k]["ms_per_epoch"])
     ms_epoch = runs[best]["ms_per_epoch"]
@@ -351,7 +352,10 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
         d_src = torch.empty_like(src); d_lab = torch.empty_like(labels)
         net = sz.SimpleNeuralNet(60, 512, 256, MLP_SPEAKERS, seed=7, ctx=ctx)
         if world > 1:
-            ctx.comm_peer_exchange(best.startswith("two-shot"))
+            if best.startswith("NCCL"):
+                ctx.comm_peer_exchange(False)
+            else:
+                ctx.comm_peer_exchange(True, best.split(" ")[0])
         def e2e_epoch(n_rows):
             N.check(N.lib.szb_memcpy_h2d(ctx.handle, C.c_void_p(d_src.data_ptr()), C.c_void_p(h_src.data_ptr()), nwin * 240))
             N.check(N.lib.szb_memcpy_h2d(ctx.handle, C.c_void_p(d_lab.data_ptr()), C.c_void_p(h_lab.data_ptr()), nwin * 4))

@@ -270,13 +270,19 @@ szb_status szb_comm_unique_id(uint8_t id[128]);
 szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
 szb_status szb_comm_destroy(szb_ctx* ctx);
 int32_t szb_comm_world(const szb_ctx* ctx);
-/* Alternative gradient exchange (collective call: every rank, same `enable`): every rank's gradient buffers are mapped into
- * all ranks with CUDA IPC and ONE kernel per step publishes a flag, waits for the peers, sums their gradients straight out
- * of NVLink peer memory in rank order and applies the SGD update -- no NCCL call inside a step.  Results equal the NCCL
- * path's up to float reassociation.  Opt-in (the set-up is itself a collective call), but the faster exchange at every size
- * measured on 8 x B200: 126 / 134 / 175 us per batch-4096 step at N = 2 / 4 / 8 against 146 / 158 / 180 us with the
- * overlapped NCCL all-reduces (DESIGN.md "Multi-GPU").  *active reports whether the mapping succeeded on all ranks. */
+/* Gradient exchange over NVLink peer memory, fused into the update kernel (collective call: every rank, same `enable`): every
+ * rank's exchange region is mapped into all ranks with CUDA IPC and the SGD kernel itself all-reduces the step's gradient with
+ * posted peer stores and flag rounds -- no NCCL call inside a step.  enable: 0 = off (NCCL all-reduces),
+ * 1 = on, protocol chosen by size; 2 = on, ONE-SHOT (every rank stores its whole vector into every peer, one flag round,
+ * every rank adds the vectors in rank order while it updates); 3 = on, TWO-SHOT (scatter slices, owner reduces in rank order
+ * and broadcasts, two flag rounds).  Replicas stay bit-identical with either.  *active reports whether the mapping succeeded
+ * on all ranks (otherwise every rank stays on NCCL). */
 szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active);
+
+/* Diagnostics of the fused exchange: enable != 0 starts (and clears) the recording of the phase times of the update kernel's
+ * CTA 0; ns[0..5] = mean nanoseconds per step in: scatter stores, first publish, wait for flag1, reduce + broadcast, second
+ * publish, wait for flag2; ns[7] = steps recorded since the last call. */
+szb_status szb_comm_peer_trace(szb_ctx* ctx, int32_t enable, double* ns /* [8], may be NULL */);
 
 /* ---- on-disk formats (host code) ----------------------------------------------------------------------------------- */
 /* feature_cache/<sanitised path>.npy (lib.rs:550-579): C-order <f4 [n][60]. */

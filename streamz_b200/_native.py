@@ -111,6 +111,7 @@ SIGNATURES = {
     "szb_comm_destroy": (i32, [vp]),
     "szb_comm_world": (i32, [vp]),
     "szb_comm_peer_exchange": (i32, [vp, i32, P(i32)]),
+    "szb_comm_peer_trace": (i32, [vp, i32, vp]),
     "szb_feature_cache_path": (i32, [C.c_char_p, vp, sz]),
     "szb_npy_write_f32": (i32, [C.c_char_p, vp, u64, u64]),
     "szb_npy_read_f32": (i32, [C.c_char_p, vp, u64, P(u64), P(u64)]),

@@ -106,11 +106,13 @@ class Context:
         N.check(N.lib.szb_comm_init(self.handle, buf, int(rank), int(world)))
 
 
-def _ctx_peer_exchange(self, enable: bool) -> bool:
-    """Collective: switch the gradient exchange between NCCL all-reduces (default) and the fused peer-memory kernel
-    (include/streamz_b200.h, szb_comm_peer_exchange).  Returns whether the peer exchange is active."""
+def _ctx_peer_exchange(self, enable, mode: str = "auto") -> bool:
+    """Collective: switch the gradient exchange between NCCL all-reduces (default) and the all-reduce over NVLink peer memory
+    fused into the update kernel (include/streamz_b200.h, szb_comm_peer_exchange); mode "auto" | "one-shot" | "two-shot".
+    Returns whether the peer exchange is active."""
     active = C.c_int32()
-    N.check(N.lib.szb_comm_peer_exchange(self.handle, 1 if enable else 0, C.byref(active)))
+    code = {"auto": 1, "one-shot": 2, "two-shot": 3}[mode] if enable else 0
+    N.check(N.lib.szb_comm_peer_exchange(self.handle, code, C.byref(active)))
     return bool(active.value)
 
 

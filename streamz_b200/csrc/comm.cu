@@ -119,7 +119,8 @@ static void p2p_teardown(szb_ctx* ctx) {
 static szb_status p2p_setup(szb_ctx* ctx) {
     const int W = ctx->world, me = ctx->rank;
     int ok = (W <= szb_ctx::kMaxPeers && g_nccl.AllGather) ? 1 : 0;
-    const size_t bytes = kP2pFlagBytes + 2 * kP2pCapFloats * sizeof(float);
+    // two-shot: [inbox: cap][red: cap]; one-shot: [2 step parities][W source ranks][cap]
+    const size_t bytes = kP2pFlagBytes + 2 * size_t(W) * kP2pCapFloats * sizeof(float);
     cudaIpcMemHandle_t mine{};
     if (ok && cudaMalloc(&ctx->p2p_region, bytes) != cudaSuccess) { ctx->p2p_region = nullptr; ok = 0; }
     if (ok && cudaMemset(ctx->p2p_region, 0, bytes) != cudaSuccess) ok = 0;
@@ -162,8 +163,8 @@ static szb_status p2p_setup(szb_ctx* ctx) {
         p2p_teardown(ctx);
         return SZB_OK;
     }
-    SZB_TRY(ctx->p2p_counters.reserve(2 * sizeof(unsigned int)));
-    SZB_CUDA(cudaMemset(ctx->p2p_counters.ptr, 0, 2 * sizeof(unsigned int)));
+    SZB_TRY(ctx->p2p_counters.reserve(128));            // [0, 8): tickets; [64, 128): phase trace (8 x u64)
+    SZB_CUDA(cudaMemset(ctx->p2p_counters.ptr, 0, 128));
     ctx->p2p_on = true;
     ctx->p2p_cap = kP2pCapFloats;
     ctx->p2p_step = 0;
@@ -200,6 +201,7 @@ szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int3
 
 szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active) {
     SZB_REQUIRE(ctx, "szb_comm_peer_exchange: ctx is NULL");
+    if (enable >= 1 && enable <= 3) ctx->p2p_mode = enable == 1 ? 0 : enable - 1;      // 1: choose by size, 2: one-shot, 3: two-shot
     if (ctx->world > 1 && ctx->nccl_comm) {
         SZB_CUDA(cudaSetDevice(ctx->device));
         if (enable && !ctx->p2p_on) SZB_TRY(p2p_setup(ctx));
@@ -212,6 +214,23 @@ szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active)
         }
     }
     if (active) *active = ctx->p2p_on ? 1 : 0;
+    return SZB_OK;
+}
+
+// Diagnostics of the fused exchange: enable != 0 starts recording (and clears) the phase times of CTA 0 of the update kernel;
+// ns[0..5] = mean nanoseconds per step spent in: scatter stores, first publish (fence + ticket + flag), wait for flag1, reduce +
+// broadcast, second publish, wait for flag2; ns[6] = 0; ns[7] = steps recorded.
+szb_status szb_comm_peer_trace(szb_ctx* ctx, int32_t enable, double* ns) {
+    SZB_REQUIRE(ctx, "szb_comm_peer_trace: ctx is NULL");
+    if (!ctx->p2p_on) { if (ns) for (int i = 0; i < 8; ++i) ns[i] = 0.0; return SZB_OK; }
+    SZB_CUDA(cudaSetDevice(ctx->device));
+    SZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[8] = {};
+    unsigned char* base = ctx->p2p_counters.as<unsigned char>() + 64;
+    SZB_CUDA(cudaMemcpy(h, base, sizeof h, cudaMemcpyDeviceToHost));
+    if (ns) for (int i = 0; i < 8; ++i) ns[i] = i == 7 ? double(h[7]) : (h[7] ? double(h[i]) / double(h[7]) : 0.0);
+    SZB_CUDA(cudaMemset(base, 0, sizeof h));
+    ctx->p2p_trace_on = enable != 0;
     return SZB_OK;
 }
 

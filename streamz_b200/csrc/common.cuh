@@ -128,6 +128,8 @@ struct szb_ctx {
     uint32_t* p2p_flags[kMaxPeers] = {};      // flag block of every rank: [s] / [16 + s] = last step rank s finished phase 0 / 1 for
     szb::DevBuf p2p_counters;                 // private last-CTA tickets of the two phases
     int p2p_max_blocks = 0;                   // co-resident CTA capacity of the update kernels (0 = not queried yet)
+    int p2p_mode = 0;                         // 0 = by size (one-shot below 6 MB of outgoing copies per step), 1 = one-shot, 2 = two-shot
+    bool p2p_trace_on = false;                // szb_comm_peer_trace: CTA 0 of the update kernel records its phase times
     void* p2p_region = nullptr;               // local allocation backing p2p_flags / p2p_inbox / p2p_red of this rank
 };
 

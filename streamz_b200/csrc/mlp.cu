@@ -382,10 +382,14 @@ __global__ void sgd_kernel(float* __restrict__ params, const float* __restrict__
 // publishes flag2(t) only after it has finished reading its inbox(t); `red` of rank d is rewritten in phase 1 of step t+1,
 // which the writers enter only after flag1(t+1) from d, i.e. after d's step-t kernel (the reader of red) has completed.
 struct P2pArgs {
-    float* inbox[szb_ctx::kMaxPeers];        // inbox of every rank: [world][slice_g * 4] floats, row = source rank
-    float* red[szb_ctx::kMaxPeers];          // reduced-vector buffer of every rank
+    float* inbox[szb_ctx::kMaxPeers];        // two-shot: inbox of every rank: [world][slice_g * 4] floats, row = source rank
+    float* red[szb_ctx::kMaxPeers];          // two-shot: reduced-vector buffer of every rank
+    float* area[szb_ctx::kMaxPeers];         // one-shot: [2 (step parity)][world (source rank)][cap] full gradient vectors
+    size_t cap;                              // floats per vector slot of `area`
+    int one_shot;                            // 1: every rank stores its WHOLE vector into every peer (one flag round)
     uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank: [0, 16) flag1 per source rank, [16, 32) flag2
     unsigned int* counters;                  // private: [0] CTAs done with phase 0, [1] with phase 1 (last-CTA detection)
+    unsigned long long* trace;               // optional (szb_comm_peer_trace): CTA 0 accumulates %globaltimer deltas per phase
     int rank, world;
     uint32_t step;
     uint32_t n4, slice_g;                    // 16-byte groups in V, groups per slice
@@ -424,18 +428,48 @@ __device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* coun
         if (s_last) *counter = 0u;                         // every CTA has arrived; the next step finds it zero
     }
     __syncthreads();
-    if (s_last && int(threadIdx.x) < a.world) {
-        __threadfence_system();
+    if (s_last && int(threadIdx.x) < a.world)      // (the release store orders everything the barrier above made visible to this thread)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + flag_base + a.rank), "r"(a.step) : "memory");
-    }
 }
 
 // Phases 0 and 1.  On return (all threads of the CTA) the local `red` buffer holds the rank-ordered sum of every rank's
 // V; read it with L1-bypassing loads (peers wrote it).
+__device__ __forceinline__ unsigned long long p2p_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// trace slot i accumulates the nanoseconds CTA 0 spent up to the end of phase part i (0 scatter, 1 publish, 2 wait flag1,
+// 3 reduce + broadcast, 4 publish, 5 wait flag2); slot 7 counts the steps
+#define P2P_TRACE(i) do { if (tr) { const unsigned long long tn = p2p_now(); atomicAdd(a.trace + (i), tn - t_prev); t_prev = tn; } } while (0)
+
 __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const float* __restrict__ G) {
     const int me = a.rank, W = a.world;
+    const bool tr = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long t_prev = tr ? p2p_now() : 0ull;
     const size_t nthreads = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const float4* G4 = reinterpret_cast<const float4*>(G);
+    if (a.one_shot) {
+        // ONE-SHOT: the whole vector goes to every peer (W - 1 posted stores per 16-byte group), one flag round, and every rank
+        // adds the W vectors itself while it updates (p2p_grad_at).  Moves (W - 1) x the vector per rank instead of 2 (W - 1) / W,
+        // but saves a whole publish / wait round (~12 us): the faster exchange while the vector is small against the link
+        // (753 KB x 7 peers = 7 us of NVLink time at W = 8).  Slots alternate by step parity: a rank overwrites slot p two steps
+        // later, after every peer has published the step in between, i.e. has finished the update that read slot p.
+        const size_t slot4 = (size_t(a.step & 1u) * W + me) * (a.cap / 4);
+        for (size_t i = t0; i < a.n4; i += nthreads) {
+            const float4 v = G4[i];
+#pragma unroll
+            for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+                if (r < W && r != me) reinterpret_cast<float4*>(a.area[r])[slot4 + i] = v;
+        }
+        P2P_TRACE(0);
+        p2p_publish(a, a.counters + 0, 0);
+        P2P_TRACE(1);
+        p2p_wait_flags(a.flags[me], W, a.step);
+        P2P_TRACE(2);
+        if (tr) atomicAdd(a.trace + 7, 1ull);
+        return nullptr;
+    }
     // ---- phase 0: scatter my slices to their owners (my own slice stays in G)
     for (size_t i = t0; i < a.n4; i += nthreads) {
         const uint32_t d = uint32_t(i / a.slice_g);
@@ -443,9 +477,12 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
         const float4 v = G4[i];
         reinterpret_cast<float4*>(a.inbox[d])[size_t(me) * a.slice_g + (i - size_t(d) * a.slice_g)] = v;
     }
+    P2P_TRACE(0);
     p2p_publish(a, a.counters + 0, 0);
+    P2P_TRACE(1);
     // ---- phase 1: reduce my slice in rank order, broadcast it
     p2p_wait_flags(a.flags[me], W, a.step);
+    P2P_TRACE(2);
     const size_t g0 = size_t(me) * a.slice_g;
     const size_t mine = g0 < a.n4 ? min(size_t(a.slice_g), size_t(a.n4) - g0) : 0;
     const float4* in4 = reinterpret_cast<const float4*>(a.inbox[me]);
@@ -462,10 +499,30 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
         for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
             if (r < W) reinterpret_cast<float4*>(a.red[r])[g0 + o] = s;
     }
+    P2P_TRACE(3);
     p2p_publish(a, a.counters + 1, 16);
+    P2P_TRACE(4);
     // ---- phase 2 entry: everybody's reduced slice has landed here
     p2p_wait_flags(a.flags[me] + 16, W, a.step);
+    P2P_TRACE(5);
+    if (tr) atomicAdd(a.trace + 7, 1ull);
     return a.red[me];
+}
+
+// Element idx of the step's reduced gradient after p2p_exchange: the two-shot exchange left it in R; after the one-shot
+// exchange it is the rank-ordered sum of this rank's private value and the peers' copies in the local area.
+__device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __restrict__ R, const float* __restrict__ G, size_t idx) {
+    if (!a.one_shot) return __ldcg(R + idx);
+    const float* base = a.area[a.rank] + size_t(a.step & 1u) * a.world * a.cap + idx;
+    float v[szb_ctx::kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+        if (r < a.world) v[r] = r == a.rank ? G[idx] : __ldcg(base + size_t(r) * a.cap);
+    float s = v[0];
+#pragma unroll
+    for (int r = 1; r < szb_ctx::kMaxPeers; ++r)
+        if (r < a.world) s += v[r];
+    return s;
 }
 
 // Tensor-core path: the SGD update, the refresh of the transposed weight copies the GEMMs read, and the zeroing of the
@@ -485,7 +542,7 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     tc::pdl_wait();
     const bool peers = a.world > 1;
     const float* R = peers ? p2p_exchange(a, G) : G;     // the step's (reduced) gradient vector
-    auto grad_at = [&](size_t idx) -> float { return peers ? __ldcg(R + idx) : R[idx]; };
+    auto grad_at = [&](size_t idx) -> float { return peers ? p2p_grad_at(a, R, G, idx) : R[idx]; };
     const float n_used = grad_at(np + 4 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (stats) {
@@ -543,7 +600,7 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
 __global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params, const float* __restrict__ G,
                                                       const __grid_constant__ P2pArgs a, size_t n, float lr, double* __restrict__ stats) {
     const float* R = p2p_exchange(a, G);
-    const float n_used = __ldcg(R + n), loss = __ldcg(R + n + 1);
+    const float n_used = p2p_grad_at(a, R, G, n), loss = p2p_grad_at(a, R, G, n + 1);
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
         stats[0] += double(loss);
         stats[1] += double(n_used);
@@ -551,7 +608,7 @@ __global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params
     if (n_used <= 0.f) return;             // empty global batch: no-op (lib.rs:1003-1005)
     const float scale = lr / n_used;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
-        params[i] -= __ldcg(R + i) * scale;
+        params[i] -= p2p_grad_at(a, R, G, i) * scale;
 }
 
 __global__ void init_uniform_kernel(float* __restrict__ w, size_t n, unsigned long long key, unsigned long long base) {
@@ -884,9 +941,14 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         for (int r = 0; r < ctx->world; ++r) {
             a.inbox[r] = ctx->p2p_inbox[r];
             a.red[r] = ctx->p2p_red[r];
+            a.area[r] = ctx->p2p_inbox[r];
             a.flags[r] = ctx->p2p_flags[r];
         }
+        a.cap = ctx->p2p_cap;
+        // one round of flags instead of two while (world - 1) copies of the vector are a few microseconds of NVLink time
+        a.one_shot = ctx->p2p_mode == 1 || (ctx->p2p_mode == 0 && size_t(ctx->world - 1) * nv * sizeof(float) <= (size_t(6) << 20)) ? 1 : 0;
         a.counters = ctx->p2p_counters.as<unsigned int>();
+        a.trace = ctx->p2p_trace_on ? reinterpret_cast<unsigned long long*>(ctx->p2p_counters.as<unsigned char>() + 64) : nullptr;
         a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
         // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
         if (ctx->p2p_max_blocks == 0) {

@@ -41,15 +41,18 @@ def _worker(rank, world, port, tmp):
         tot += loss; cnt += used
     # the same two epochs again with the two-shot peer-memory exchange fused into the update kernel instead of NCCL,
     # on the tensor-core path (sgd_fused_kernel) and on the FP32 CUDA-core path (sgd_p2p_kernel)
-    peer = ctx.comm_peer_exchange(True)
-    w2, w3 = None, None
-    for mode in ("3xtf32", "fp32"):
+    w2, w3, w4 = None, None, None
+    peer = True
+    for mode, proto in (("3xtf32", "one-shot"), ("3xtf32", "two-shot"), ("fp32", "auto")):
+        peer = ctx.comm_peer_exchange(True, proto) and peer
         net2 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx).set_precision(mode)
         for epoch in range(2):
             local, sizes = shard_batches(d[f"perm{epoch}"], 96, rank, world)
             sz.train_epoch_steps(net2, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
-        if mode == "3xtf32":
+        if proto == "one-shot":
             w2 = net2.weights()
+        elif proto == "two-shot":
+            w4 = net2.weights()
         else:
             w3 = net2.weights()
     ctx.comm_peer_exchange(False)
@@ -58,7 +61,7 @@ def _worker(rank, world, port, tmp):
     lo, hi = shard_clips([len(c) for c in clips], world)[rank]
     feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
     np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)},
-             **{f"r{i}": w for i, w in enumerate(w3)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+             **{f"r{i}": w for i, w in enumerate(w3)}, **{f"s{i}": w for i, w in enumerate(w4)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
     dist.destroy_process_group()
 
 
@@ -99,8 +102,11 @@ def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp
             assert np.abs(outs[k][f"r{i}"] - w).max() <= 1e-5             # FP32 path: sgd_p2p_kernel
     for k in range(1, world):
         for i in range(6):                                                # every slice is summed once, in rank order, and
-            assert np.array_equal(outs[0][f"q{i}"], outs[k][f"q{i}"])     # broadcast: bit-identical replicas
-            assert np.array_equal(outs[0][f"r{i}"], outs[k][f"r{i}"])
+            assert np.array_equal(outs[0][f"q{i}"], outs[k][f"q{i}"])     # broadcast (two-shot) or summed by every rank in the same
+            assert np.array_equal(outs[0][f"r{i}"], outs[k][f"r{i}"])     # order (one-shot): bit-identical replicas
+            assert np.array_equal(outs[0][f"s{i}"], outs[k][f"s{i}"])
+    for i in range(6):
+        assert np.array_equal(outs[0][f"q{i}"], outs[0][f"s{i}"])         # the two protocols add in the same order: same bits
     single = sz.FeatureExtractor(ctx).extract_batch(clips)
     seen = 0
     for k in range(world):

@@ -23,17 +23,23 @@ perm = np.random.default_rng(5).permutation(nwin).astype(np.uint32)
 loss, used = C.c_double(), C.c_uint64()
 modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 4]
 for mode in modes:
-    peer = ctx.comm_peer_exchange(bool(mode & 4))      # mode 4: fused peer-memory exchange instead of NCCL
+    peer = ctx.comm_peer_exchange(bool(mode & 4), {4: "two-shot", 5: "one-shot"}.get(mode, "auto"))   # 4 / 5: fused peer exchange; 0: NCCL
     net = sz.SimpleNeuralNet(60, 512, 256, 100, seed=7, ctx=ctx)
     def epoch(n_rows):
         N.check(N.lib.szb_net_train_epoch_dev(net._h, C.c_void_p(src.data_ptr()), C.c_void_p(labels.data_ptr()), nwin, N.ptr(perm),
                                               n_rows, batch, 0.01, 0.2, 99, 0, None, C.byref(loss), C.byref(used)))
     epoch(batch * 8)
     dist.barrier()
+    tr = np.zeros(8, np.float64)
+    N.check(N.lib.szb_comm_peer_trace(ctx.handle, 1, N.ptr(tr)))
     ctx.timer_start(); t0 = time.perf_counter()
     epoch(nwin)
     wall = (time.perf_counter() - t0) * 1e3
     ms = ctx.timer_stop()
+    N.check(N.lib.szb_comm_peer_trace(ctx.handle, 0, N.ptr(tr)))
+    if peer:
+        print(f"  rank {rank} exchange phases, mean us per step over {int(tr[7])} steps (CTA 0): scatter {tr[0]/1e3:.2f}, publish1 {tr[1]/1e3:.2f}, "
+              f"wait1 {tr[2]/1e3:.2f}, reduce+bcast {tr[3]/1e3:.2f}, publish2 {tr[4]/1e3:.2f}, wait2 {tr[5]/1e3:.2f}  (sum {tr[:6].sum()/1e3:.2f})", flush=True)
     t = torch.tensor([ms, wall], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
