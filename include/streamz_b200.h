@@ -76,6 +76,9 @@ szb_status szb_ctx_set_fused_resample(szb_ctx* ctx, int32_t enable);
 szb_status szb_ctx_set_l2_ring(szb_ctx* ctx, int32_t chunk_mb, int32_t streams);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 uint64_t szb_ctx_launch_count(const szb_ctx* ctx);
+/* Of those, how many two-step training graphs were replayed with cudaGraphLaunch (small-batch epochs; each replay stands for
+ * 22 kernels in the count above). */
+uint64_t szb_ctx_graph_launch_count(const szb_ctx* ctx);
 /* Device-time of the work enqueued between start and stop on the context's stream (CUDA events). */
 szb_status szb_timer_start(szb_ctx* ctx);
 szb_status szb_timer_stop(szb_ctx* ctx, float* elapsed_ms);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "szb_ctx_set_fused_resample": (i32, [vp, i32]),
     "szb_ctx_set_l2_ring": (i32, [vp, i32, i32]),
     "szb_ctx_launch_count": (u64, [vp]),
+    "szb_ctx_graph_launch_count": (u64, [vp]),
     "szb_timer_start": (i32, [vp]),
     "szb_timer_stop": (i32, [vp, P(f32)]),
     "szb_kernel_timing": (i32, [vp, i32]),

@@ -151,6 +151,7 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
+    if (const char* e = getenv("SZB_NO_GRAPHS")) ctx->graphs = !(e[0] == '1');
     if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_CHUNK_MB")) ctx->l2_chunk_mb = std::max(0, atoi(e));
     if (const char* e = getenv("SZB_FUSED_RESAMPLE")) ctx->fuse_resample = (e[0] == '1');
@@ -223,6 +224,7 @@ szb_status szb_ctx_set_l2_ring(szb_ctx* ctx, int32_t chunk_mb, int32_t streams) 
     return SZB_OK;
 }
 uint64_t szb_ctx_launch_count(const szb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t szb_ctx_graph_launch_count(const szb_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
 
 szb_status szb_timer_start(szb_ctx* ctx) {
     SZB_REQUIRE(ctx, "szb_timer_start: ctx is NULL");

@@ -81,6 +81,8 @@ struct szb_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // chunk pipeline of the host entry points
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
     uint64_t launches = 0;
+    uint64_t graph_launches = 0;   // cudaGraphLaunch calls (captured two-step training graphs)
+    bool graphs = true;   // small-batch training epochs replay a captured two-step CUDA graph (SZB_NO_GRAPHS=1 turns it off)
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
     bool gemm_ta = true;    // dense-layer GEMMs take the A operand from tensor memory (gemm_tc_ta_kernel); SZB_GEMM_TA=0 selects the
                             // shared-memory-operand kernel (round 2: full GPU suite green with it, 97.1 vs 101.0 us per batch-4096 step)

@@ -303,10 +303,14 @@ __global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_
                                   int keep_by_row /* keep indexed by window id (1) or by batch row (0) */, float prob,
                                   unsigned long long key, float* __restrict__ xb, float* __restrict__ xbT, uint32_t* __restrict__ lab,
                                   uint8_t* __restrict__ valid, float* __restrict__ h1T, int h1, float* __restrict__ h2T, int h2,
-                                  int use_tile) {
+                                  int use_tile, const StepParams* __restrict__ sp) {
     extern __shared__ float prep_tile[];   // [n_in][33] when use_tile
     tc::pdl_launch_dependents();
     tc::pdl_wait();
+    if (sp) {                              // captured step: position in the shuffled order and dropout key come from device memory
+        perm += sp->cursor;
+        key = sp->key;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int row0 = blockIdx.x * 32;
     for (int r = warp; r < 32; r += nw) {
@@ -536,10 +540,15 @@ __device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __re
 __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ WT, int n_in,
                                                         int h1, int h2, int n_out, size_t off_b1, size_t off_w2, size_t off_b2,
                                                         size_t off_w3, size_t off_b3, size_t off_wt2, size_t off_wt3, size_t np, int parity,
-                                                        float lr, double* __restrict__ stats, const __grid_constant__ P2pArgs a) {
+                                                        float lr, double* __restrict__ stats, const __grid_constant__ P2pArgs a,
+                                                        StepParams* __restrict__ sp, int advance) {
     __shared__ float tile[32][33];
     tc::pdl_launch_dependents();
     tc::pdl_wait();
+    if (sp) {                              // captured step (CUDA graph): learning rate from device memory; move on to the next batch
+        lr = sp->lr;                       // (the next step's batch kernel reads the position only after this grid has completed)
+        if (blockIdx.x == 0 && threadIdx.x == 0) sp->cursor += uint32_t(advance);
+    }
     const bool peers = a.world > 1;
     const float* R = peers ? p2p_exchange(a, G) : G;     // the step's (reduced) gradient vector
     auto grad_at = [&](size_t idx) -> float { return peers ? p2p_grad_at(a, R, G, idx) : R[idx]; };
@@ -828,7 +837,7 @@ szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n);  // comm.cu
 szb_status comm_allreduce_overlapped(szb_ctx* ctx, float* buf, size_t n);
 szb_status comm_join(szb_ctx* ctx);
 
-static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr) {
+static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr, StepParams* sp = nullptr) {
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
     const size_t np = net->n_params();
@@ -967,7 +976,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         if (p2p) blocks = std::min(blocks, p2p_blocks);
         SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
                             int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
-                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a));
+                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a, sp, B));
     } else if (p2p) {
         const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(std::min(ctx->sm_count * 2, p2p_blocks))));
         sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, G, a, np, lr, net->stats.as<double>());
@@ -988,7 +997,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
 }
 
 static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, int B,
-                              const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key) {
+                              const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key, const StepParams* sp = nullptr) {
     if (B <= 0) return SZB_OK;
     const int wpb = B >= 32 ? 32 : 8;     // one warp per row when the block's 32 rows exist: every gather load in flight at once
     const size_t tile_bytes = size_t(net->n_in) * 33 * sizeof(float);
@@ -996,8 +1005,38 @@ static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t
     SZB_CUDA(launch_pdl(net->ctx, prep_batch_kernel, dim3((B + 31) / 32), dim3(wpb * 32), use_tile ? tile_bytes : size_t(0), d_feats,
                         d_labels, d_perm, B, int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
                         net->precision != 0 ? net->xbT.as<float>() : nullptr, net->lab.as<uint32_t>(), net->valid.as<uint8_t>(),
-                        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2), use_tile));
+                        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2), use_tile, sp));
     net->ctx->launches += 1;
+    return SZB_OK;
+}
+
+// Small batches are launch-latency-bound (11 kernels per step, a few microseconds of work each; BASELINE configs[0]: batch 8):
+// two consecutive steps (one of each tail parity) are captured ONCE as a CUDA graph -- programmatic dependent launch edges
+// included -- and replayed for the rest of the epoch and for later epochs; what changes from step to step or epoch to epoch
+// (position in the permutation, dropout key, learning rate) is read from StepParams in device memory.
+static szb_status capture_step_graph(szb_net* net, const StepGraphKey& k, float prob) {
+    szb_ctx* ctx = net->ctx;
+    if (net->step_graph) { cudaGraphExecDestroy(net->step_graph); net->step_graph = nullptr; }
+    const uint64_t launches0 = ctx->launches;
+    StepParams* sp = net->step_params.as<StepParams>();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); net->step_graph_failed = true; return SZB_OK; }
+    szb_status st = SZB_OK;
+    for (int rep = 0; rep < 2 && st == SZB_OK; ++rep) {
+        st = launch_prep(net, static_cast<const float*>(k.feats), static_cast<const uint32_t*>(k.labels), static_cast<const uint32_t*>(k.perm), k.B,
+                         static_cast<const uint8_t*>(k.keep), 1, prob, 0ull, sp);
+        if (st == SZB_OK) st = train_step_staged(net, k.B, nullptr, 0.f, sp);
+    }
+    const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->launches = launches0;                          // nothing ran
+    if (st != SZB_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&net->step_graph, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        net->step_graph = nullptr;
+        net->step_graph_failed = true;                  // e.g. a driver without programmatic edges in captured graphs: stay on plain launches
+    } else {
+        net->step_graph_key = k;
+    }
+    if (graph) cudaGraphDestroy(graph);
     return SZB_OK;
 }
 
@@ -1120,6 +1159,8 @@ szb_status szb_net_add_output_class(szb_net* net, const float* new_col, uint64_t
 void szb_net_destroy(szb_net* net) {
     if (!net) return;
     if (net->ctx) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); }
+    if (net->step_graph) cudaGraphExecDestroy(net->step_graph);
+    net->step_params.release();
     for (DevBuf* b : { &net->params, &net->grads, &net->xb, &net->lab, &net->valid, &net->a_h1, &net->a_h2, &net->a_z, &net->d_2,
                        &net->d_1, &net->stats, &net->perm, &net->hist, &net->wt, &net->xbT, &net->h1T, &net->h2T, &net->zT, &net->d2T, &net->d1T })
         b->release();
@@ -1245,12 +1286,47 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
     const unsigned long long key = dropout_key(seed, stream);
     uint64_t s = 0;
-    for (uint32_t i = 0; i < n_steps; ++i) {
+    uint32_t i = 0;
+    auto plain_step = [&]() -> szb_status {
         const int B = int(step_sizes[i]);
         SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
         SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
         s += step_sizes[i];
+        ++i;
+        return SZB_OK;
+    };
+    // ---- small batches: replay a captured two-step graph (see capture_step_graph) -------------------------------------------
+    const int B0 = int(step_sizes[0]);
+    uint32_t n_full = 0;
+    while (n_full < n_steps && int(step_sizes[n_full]) == B0) ++n_full;
+    if (ctx->graphs && ctx->world == 1 && net->precision != 0 && !net->step_graph_failed && B0 > 0 && B0 <= 256 && n_full >= 8) {
+        SZB_TRY(net->step_params.reserve(sizeof(StepParams)));
+        StepGraphKey k;
+        k.B = B0; k.precision = net->precision; k.feats = d_feats; k.labels = d_labels; k.keep = d_keep; k.perm = net->perm.ptr;
+        k.params = net->params.ptr; k.prob = dropout; k.cap_rows = net->cap_rows; k.n_out = net->n_out;
+        if (!net->grads_zero || net->wt_dirty) {       // the first steps of a net run plainly: they set up the state a captured step assumes
+            SZB_TRY(plain_step());
+            SZB_TRY(plain_step());
+        }
+        k.parity = net->step_graph ? net->step_graph_key.parity : net->tail_parity;
+        if (net->step_graph && net->step_graph_key == k && net->tail_parity != k.parity) SZB_TRY(plain_step());   // an odd step count left the
+        k.parity = net->tail_parity;                                                                            // other tail block current
+        if (!net->step_graph || !(net->step_graph_key == k)) SZB_TRY(capture_step_graph(net, k, dropout));
+        if (net->step_graph && net->step_graph_key == k) {
+            const uint32_t n_pairs = (n_full - i) / 2;
+            void* hp = nullptr;
+            SZB_TRY(ctx->h_stage.acquire(sizeof(StepParams), &hp));
+            *static_cast<StepParams*>(hp) = StepParams{ uint32_t(s), lr, key };
+            SZB_CUDA(cudaMemcpyAsync(net->step_params.ptr, hp, sizeof(StepParams), cudaMemcpyHostToDevice, ctx->stream));
+            SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
+            for (uint32_t p = 0; p < n_pairs; ++p) SZB_CUDA(cudaGraphLaunch(net->step_graph, ctx->stream));
+            ctx->launches += uint64_t(n_pairs) * 22;     // 2 x (batch kernel, 8 GEMMs, softmax, update)
+            ctx->graph_launches += n_pairs;
+            i += 2 * n_pairs;
+            s += uint64_t(2 * n_pairs) * uint64_t(B0);
+        }
     }
+    while (i < n_steps) SZB_TRY(plain_step());
     return read_stats(net, loss_sum, n_used);   // loss and count are global (all-reduced) in a multi-GPU run
 }
 

@@ -2,6 +2,28 @@
 #pragma once
 #include "common.cuh"
 
+namespace szb {
+// Per-epoch parameters of a CAPTURED training step (CUDA graph): they live in device memory so that one instantiated graph
+// serves every step of every epoch -- the batch kernel reads its position in the shuffled order and the dropout key from here,
+// the update kernel the learning rate, and it advances the position for the next step.
+struct StepParams {
+    uint32_t cursor;              // first row of the step in the epoch's permutation
+    float lr;
+    unsigned long long key;       // dropout key of the epoch (seed, stream)
+};
+struct StepGraphKey {             // everything a captured step bakes in
+    int B = 0, precision = -1, parity = -1;
+    const void *feats = nullptr, *labels = nullptr, *keep = nullptr, *perm = nullptr, *params = nullptr;
+    float prob = -1.f;
+    uint64_t cap_rows = 0;
+    uint32_t n_out = 0;
+    bool operator==(const StepGraphKey& o) const {
+        return B == o.B && precision == o.precision && parity == o.parity && feats == o.feats && labels == o.labels && keep == o.keep &&
+               perm == o.perm && params == o.params && prob == o.prob && cap_rows == o.cap_rows && n_out == o.n_out;
+    }
+};
+}  // namespace szb
+
 struct szb_net {
     szb_ctx* ctx = nullptr;
     uint32_t n_in = 0, h1 = 0, h2 = 0, n_out = 0;
@@ -18,6 +40,12 @@ struct szb_net {
     int tail_parity = 0;          // which tail block the current step accumulates [n_used, loss] into
     int precision = 1;            // 0 = FP32 SIMT, 1 = 3xTF32 tensor cores (default), 2 = TF32 tensor cores
     uint64_t cap_rows = 0, cap_rows_t = 0;
+    // small-batch epochs (launch-latency-bound: 11 launches per step): two consecutive steps captured once as a CUDA graph
+    // and replayed (mlp.cu: szb_net_train_epoch_steps_dev)
+    szb::DevBuf step_params;
+    cudaGraphExec_t step_graph = nullptr;
+    szb::StepGraphKey step_graph_key;
+    bool step_graph_failed = false;
     std::vector<std::vector<std::string>> file_lists;  // lib.rs:757, host-side only
     // Saved speaker embeddings with their quality metrics (lib.rs:760-761, set_embeddings / embeddings lib.rs:870-877) and
     // the optional hidden encoding layer (lib.rs:752-754).  Host-side state that model.npz carries (lib.rs:1099-1127,

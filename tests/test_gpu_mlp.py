@@ -311,3 +311,39 @@ def test_batched_identification_equals_per_clip_histograms(sz, ctx, oracle):
             assert np.array_equal(got[c].astype(np.int64), want), (thr, c)
         assert np.array_equal(got.astype(np.int64).sum(axis=0), oracle.identify_counts(onet, np.concatenate(clips), thr)) or thr > 0.0
     assert sz.identify_counts_batch(net, [], 0.5).shape == (0, 7)
+
+
+def test_small_batch_epochs_replay_a_captured_graph_with_identical_results(sz, ctx, oracle, native, monkeypatch):
+    # Batch 8 (the reference's default, main.rs:36) is launch-latency-bound: the epoch replays a captured two-step CUDA graph.
+    # Same kernels, same order: the weights must equal those of plain launches (SZB_NO_GRAPHS=1 context) to within the order of
+    # the split-K reductions, and the oracle's to 1e-4, over several epochs with odd step counts and a ragged last batch.
+    r = np.random.default_rng(3)
+    n = 8 * 37 + 5
+    feats = r.standard_normal((n, 60)).astype(np.float32)
+    labels = r.integers(0, 3, n).astype(np.uint32)
+    onet = oracle.Net.init(60, 512, 256, 3, seed=2)
+    perms = [r.permutation(n).astype(np.uint32) for _ in range(3)]
+    monkeypatch.setenv("SZB_NO_GRAPHS", "1")
+    plain_ctx = sz.Context(0)
+    monkeypatch.delenv("SZB_NO_GRAPHS")
+    results = []
+    for c in (ctx, plain_ctx):
+        net = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=c)
+        data = sz.DeviceFeatures(c, feats, labels)
+        tot, cnt = 0.0, 0
+        launches0 = c.launch_count
+        for e, perm in enumerate(perms):
+            loss, used = sz.train_epoch(net, data, perm, 8, 0.01 * 0.99 ** e, dropout=0.2, seed=5, stream=e)   # lr and key change per epoch
+            tot += loss; cnt += used
+        results.append((net.weights(), tot, cnt, c.launch_count - launches0, int(native.lib.szb_ctx_graph_launch_count(c.handle))))
+        data.close()
+        net.close()                                            # a net must not outlive its context
+    (wg, lg, cg, ng, gg), (wp, lp, cp, npl, gp) = results
+    assert gg > 0 and gp == 0                                  # the default context really replayed graphs, the other one did not
+    assert cg == cp and abs(lg - lp) <= 1e-4 * abs(lp) and ng == npl                      # same work, same launch count claimed
+    assert max(float(np.abs(a - b).max()) for a, b in zip(wg, wp)) <= 1e-6
+    for e, perm in enumerate(perms):
+        keep = oracle.dropout_keep_mask(5, e, np.arange(n), 60, 0.2)
+        oracle.train_epoch(onet, feats, labels, perm, 8, 0.01 * 0.99 ** e, keep)
+    assert max(float(np.abs(a - b).max()) for a, b in zip(wg, onet.params())) <= 1e-4
+    plain_ctx.close()
