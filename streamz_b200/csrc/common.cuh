@@ -82,6 +82,7 @@ struct szb_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // szb_timer_*
     uint64_t launches = 0;
     uint64_t graph_launches = 0;   // cudaGraphLaunch calls (captured two-step training graphs)
+    bool small_steps = true;   // epochs whose batches have <= 32 rows run as one persistent cooperative kernel (SZB_NO_SMALL_KERNEL=1: off)
     bool graphs = true;   // small-batch training epochs replay a captured two-step CUDA graph (SZB_NO_GRAPHS=1 turns it off)
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
     bool gemm_ta = true;    // dense-layer GEMMs take the A operand from tensor memory (gemm_tc_ta_kernel); SZB_GEMM_TA=0 selects the

@@ -1161,6 +1161,7 @@ void szb_net_destroy(szb_net* net) {
     if (net->ctx) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); }
     if (net->step_graph) cudaGraphExecDestroy(net->step_graph);
     net->step_params.release();
+    net->small_scratch.release(); net->small_barrier.release(); net->small_steps.release();
     for (DevBuf* b : { &net->params, &net->grads, &net->xb, &net->lab, &net->valid, &net->a_h1, &net->a_h2, &net->a_z, &net->d_2,
                        &net->d_1, &net->stats, &net->perm, &net->hist, &net->wt, &net->xbT, &net->h1T, &net->h2T, &net->zT, &net->d2T, &net->d1T })
         b->release();
@@ -1285,6 +1286,11 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     if (n_perm) SZB_CUDA(cudaMemcpyAsync(net->perm.ptr, perm, n_perm * 4, cudaMemcpyHostToDevice, ctx->stream));
     SZB_CUDA(cudaMemsetAsync(net->stats.ptr, 0, 2 * sizeof(double), ctx->stream));
     const unsigned long long key = dropout_key(seed, stream);
+    {   // batches of <= 32 rows (the reference's default is 8): the whole epoch in one persistent kernel (train_small.cu)
+        bool done = false;
+        SZB_TRY(train_epoch_small(net, d_feats, d_labels, net->perm.as<uint32_t>(), step_sizes, n_steps, lr, dropout, key, d_keep, &done));
+        if (done) return read_stats(net, loss_sum, n_used);
+    }
     uint64_t s = 0;
     uint32_t i = 0;
     auto plain_step = [&]() -> szb_status {

@@ -42,6 +42,10 @@ struct szb_net {
     uint64_t cap_rows = 0, cap_rows_t = 0;
     // small-batch epochs (launch-latency-bound: 11 launches per step): two consecutive steps captured once as a CUDA graph
     // and replayed (mlp.cu: szb_net_train_epoch_steps_dev)
+    // batches of <= 32 rows: the whole epoch as one persistent cooperative kernel (train_small.cu)
+    szb::DevBuf small_scratch, small_barrier, small_steps;
+    int small_grid = 0;
+    bool small_failed = false;
     szb::DevBuf step_params;
     cudaGraphExec_t step_graph = nullptr;
     szb::StepGraphKey step_graph_key;
@@ -74,4 +78,6 @@ namespace szb {
 // ever zeroed while another CTA may still be reading it.
 constexpr size_t kGradTail = 8;
 szb_status net_reserve_rows(szb_net* net, uint64_t rows);
+szb_status train_epoch_small(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, const uint32_t* step_sizes,
+                             uint32_t n_steps, float lr, float dropout, unsigned long long key, const uint8_t* d_keep, bool* done);
 }  // namespace szb

@@ -314,11 +314,12 @@ def test_batched_identification_equals_per_clip_histograms(sz, ctx, oracle):
 
 
 def test_small_batch_epochs_replay_a_captured_graph_with_identical_results(sz, ctx, oracle, native, monkeypatch):
-    # Batch 8 (the reference's default, main.rs:36) is launch-latency-bound: the epoch replays a captured two-step CUDA graph.
+    # Batches of 33..256 rows are launch-latency-bound: the epoch replays a captured two-step CUDA graph.
     # Same kernels, same order: the weights must equal those of plain launches (SZB_NO_GRAPHS=1 context) to within the order of
     # the split-K reductions, and the oracle's to 1e-4, over several epochs with odd step counts and a ragged last batch.
     r = np.random.default_rng(3)
-    n = 8 * 37 + 5
+    BATCH = 48
+    n = BATCH * 37 + 5
     feats = r.standard_normal((n, 60)).astype(np.float32)
     labels = r.integers(0, 3, n).astype(np.uint32)
     onet = oracle.Net.init(60, 512, 256, 3, seed=2)
@@ -333,7 +334,7 @@ def test_small_batch_epochs_replay_a_captured_graph_with_identical_results(sz, c
         tot, cnt = 0.0, 0
         launches0 = c.launch_count
         for e, perm in enumerate(perms):
-            loss, used = sz.train_epoch(net, data, perm, 8, 0.01 * 0.99 ** e, dropout=0.2, seed=5, stream=e)   # lr and key change per epoch
+            loss, used = sz.train_epoch(net, data, perm, BATCH, 0.01 * 0.99 ** e, dropout=0.2, seed=5, stream=e)   # lr and key change per epoch
             tot += loss; cnt += used
         results.append((net.weights(), tot, cnt, c.launch_count - launches0, int(native.lib.szb_ctx_graph_launch_count(c.handle))))
         data.close()
@@ -344,6 +345,49 @@ def test_small_batch_epochs_replay_a_captured_graph_with_identical_results(sz, c
     assert max(float(np.abs(a - b).max()) for a, b in zip(wg, wp)) <= 1e-6
     for e, perm in enumerate(perms):
         keep = oracle.dropout_keep_mask(5, e, np.arange(n), 60, 0.2)
-        oracle.train_epoch(onet, feats, labels, perm, 8, 0.01 * 0.99 ** e, keep)
+        oracle.train_epoch(onet, feats, labels, perm, BATCH, 0.01 * 0.99 ** e, keep)
     assert max(float(np.abs(a - b).max()) for a, b in zip(wg, onet.params())) <= 1e-4
+    plain_ctx.close()
+
+
+def test_persistent_small_batch_kernel_equals_the_step_kernels_and_the_oracle(sz, ctx, oracle, native, monkeypatch):
+    # Batches of <= 32 rows (the reference's default is 8, main.rs:36): the epoch runs as ONE persistent cooperative kernel
+    # (train_small.cu, FP32 CUDA cores, grid barriers between the layers).  Against the oracle: <= 1e-5 after one step, <= 1e-4
+    # after epochs; against the eleven-kernel path (SZB_NO_SMALL_KERNEL=1) within FP32 reassociation; ragged last batches, batch
+    # sizes 1 / 8 / 32, windows dropped to all-zero, labels out of range, the reference's 4-3-2-2 net, 7 and 200 classes.
+    monkeypatch.setenv("SZB_NO_SMALL_KERNEL", "1")
+    plain_ctx = sz.Context(0)
+    monkeypatch.delenv("SZB_NO_SMALL_KERNEL")
+    r = np.random.default_rng(8)
+    for dims, batch, n, prob in (((60, 512, 256, 2), 8, 8 * 9 + 3, 0.2), ((60, 512, 256, 7), 32, 32 * 3 + 1, 0.2), ((60, 512, 256, 200), 1, 5, 0.0),
+                                 ((4, 3, 2, 2), 8, 19, 0.5), ((60, 512, 256, 3), 8, 8, 0.97)):
+        feats = r.standard_normal((n, dims[0])).astype(np.float32)
+        labels = r.integers(0, dims[3] + 1, n).astype(np.uint32)          # includes label == C: all-zero target (lib.rs:592-595)
+        base = oracle.Net.init(*dims, seed=4)
+        outs = []
+        for c in (ctx, plain_ctx):
+            net = sz.SimpleNeuralNet.from_weights(*base.params(), ctx=c)
+            data = sz.DeviceFeatures(c, feats, labels)
+            l0 = c.launch_count
+            tot, cnt = 0.0, 0
+            for e in range(2):
+                perm = np.random.default_rng(e).permutation(n).astype(np.uint32)
+                loss, used = sz.train_epoch(net, data, perm, batch, 0.05, dropout=prob, seed=3, stream=e)
+                tot += loss; cnt += used
+            outs.append((net.weights(), tot, cnt, c.launch_count - l0, net.forward(feats[:4])))
+            data.close(); net.close()
+        onet = base.copy()
+        otot, ocnt = 0.0, 0
+        for e in range(2):
+            perm = np.random.default_rng(e).permutation(n).astype(np.uint32)
+            keep = oracle.dropout_keep_mask(3, e, np.arange(n), dims[0], prob)
+            l, k = oracle.train_epoch(onet, feats, labels, perm, batch, 0.05, keep)
+            otot += l; ocnt += k
+        (ws, ls, cs, launches_small, ps), (wp, lp, cp, launches_plain, pp) = outs
+        assert launches_small == 2 and launches_plain > 2, (launches_small, launches_plain)      # one launch per epoch
+        assert cs == cp == ocnt, (dims, cs, cp, ocnt)
+        assert abs(ls - otot) <= 1e-4 * max(1.0, abs(otot)) and abs(lp - otot) <= 1e-4 * max(1.0, abs(otot))
+        assert max(float(np.abs(a - b).max()) for a, b in zip(ws, onet.params())) <= 1e-4, dims
+        assert max(float(np.abs(a - b).max()) for a, b in zip(ws, wp)) <= 1e-4, dims
+        assert np.abs(ps - oracle.forward(onet, feats[:4])).max() <= 1e-4        # the tensor-core forward sees the updated weights
     plain_ctx.close()
