@@ -154,6 +154,8 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     if (const char* e = getenv("SZB_NO_GRAPHS")) ctx->graphs = !(e[0] == '1');
     if (const char* e = getenv("SZB_NO_SMALL_KERNEL")) ctx->small_steps = !(e[0] == '1');
     if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
+    if (const char* e = getenv("SZB_STEP_FUSE")) ctx->step_fuse = atoi(e) & 7;
+    if (const char* e = getenv("SZB_GEMM_TMA")) ctx->gemm_tma = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_CHUNK_MB")) ctx->l2_chunk_mb = std::max(0, atoi(e));
     if (const char* e = getenv("SZB_FUSED_RESAMPLE")) ctx->fuse_resample = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_STREAMS")) ctx->l2_streams = atoi(e) > 1 ? 2 : 1;

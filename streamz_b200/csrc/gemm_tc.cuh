@@ -29,7 +29,7 @@ constexpr int UK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
 constexpr int kStages = 2;
 constexpr int kThreadsTc = 128;
 
-enum EpiTc : int { TC_BIAS = 0, TC_BIAS_RELU = 1, TC_BIAS_TANH = 2, TC_MUL_DTANH = 3, TC_MUL_DRELU = 4, TC_ATOMIC = 5 };
+enum EpiTc : int { TC_BIAS = 0, TC_BIAS_RELU = 1, TC_BIAS_TANH = 2, TC_MUL_DTANH = 3, TC_MUL_DRELU = 4, TC_ATOMIC = 5, TC_SOFTMAX_CE = 6 };
 
 struct GemmArgs {
     const float* A; int lda;      // [M][lda]
@@ -40,6 +40,9 @@ struct GemmArgs {
     const float* aux; int ldaux;  // TRANSPOSED auxiliary activation [N][ldaux] (TC_MUL_*): aux[n][m] pairs with C[m][n]
     int M, N, K;
     int k_chunk;                  // K range per blockIdx.z (multiple of BK); == K rounded up when no split
+    // TC_SOFTMAX_CE (layer 3 of a training step, N <= BN): per-row class labels or one shared target vector, the rows that
+    // survived input dropout, and the [n_used, loss] block of the gradient vector
+    const uint32_t* labels; const float* target_vec; const uint8_t* valid; float* tail;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -292,6 +295,120 @@ __device__ __forceinline__ void tc_epilogue_staged(const GemmArgs& g, uint32_t t
             }
             __syncwarp();
         }
+    }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Layer-3 epilogue of a TRAINING step when one tile holds a whole row of logits (n_out <= BN, the CTA's n0 is 0): softmax
+// (lib.rs:1023-1026), delta3 = p - t (lib.rs:1028), the loss of the row (lib.rs:611-615) and the count of rows that survived
+// input dropout (lib.rs:607-609, 1047) straight from the accumulator -- what softmax_train_kernel did in a launch of its own.
+// A thread owns one row (its TMEM lane): the row's logits never leave tensor memory; they are read three times (maximum, sum
+// of exponentials, probabilities) instead of being kept in 128 registers.  delta3 leaves row-major through the warp's
+// shared-memory tile (C: the A operand of the next GEMM) and transposed with lanes along the rows (CT: the B operand of the
+// weight-gradient GEMM).  Called by warps 0-3 (one per TMEM lane quarter).
+__device__ __forceinline__ void tc_epilogue_softmax(const GemmArgs& g, uint32_t tmem_d, int m0, bool have_acc, float* stage) {
+    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+    const int mrow0 = m0 + q * 32, m = mrow0 + lane;
+    const uint32_t lane_addr = tmem_d + (uint32_t(q * 32) << 16);
+    const int C = g.N;
+    const bool row_ok = m < g.M;
+    const bool c_vec = g.C && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    auto logits = [&](int c0, float (&v)[32]) {      // columns [c0, c0 + 32): accumulator + bias, -inf past the last class
+        uint32_t r[32];
+        if (have_acc) {
+            tmem_ld32(lane_addr + uint32_t(c0), r);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = c0 + j < C ? __uint_as_float(r[j]) + __ldg(g.bias + c0 + j) : -INFINITY;
+    };
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32];
+        logits(c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);                      // lib.rs:1023
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32];
+        logits(c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += c0 + j < C ? expf(v[j] - mx) : 0.f;  // lib.rs:1024-1025
+    }
+    const bool ok = row_ok && (g.valid ? g.valid[m] != 0 : true);
+    const uint32_t label = (row_ok && g.labels) ? g.labels[m] : 0xffffffffu;
+    float loss = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32], d[32];
+        logits(c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n = c0 + j;
+            d[j] = 0.f;
+            if (n < C) {
+                const float p = expf(v[j] - mx) / sum;                           // lib.rs:1026
+                const float t = g.target_vec ? __ldg(g.target_vec + n) : (uint32_t(n) == label ? 1.f : 0.f);
+                d[j] = ok ? p - t : 0.f;                                         // lib.rs:1028; skipped windows contribute nothing
+                if (ok && !g.target_vec && uint32_t(n) == label) loss = -logf(fmaxf(p, 1e-12f));
+            }
+        }
+        if (g.CT && row_ok) {
+            float* tp = g.CT + size_t(c0) * g.ldct + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < C) tp[size_t(j) * g.ldct] = d[j];
+        }
+        if (g.C) {
+            float* mine = stage + lane * kEpiStride;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+            __syncwarp();
+            const int cc = (lane & 7) * 4, n = c0 + cc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), mm = mrow0 + rr;
+                const float4 w = *reinterpret_cast<const float4*>(stage + rr * kEpiStride + cc);
+                if (mm < g.M && n < C) {
+                    float* dst = g.C + size_t(mm) * g.ldc + n;
+                    if (c_vec && n + 4 <= C) {
+                        *reinterpret_cast<float4*>(dst) = w;
+                    } else {
+                        const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (n + t < C) dst[t] = e[t];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    float cnt = ok ? 1.f : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        loss += __shfl_xor_sync(0xffffffffu, loss, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0 && g.tail) {
+        if (cnt > 0.f) atomicAdd(g.tail, cnt);
+        if (loss != 0.f) atomicAdd(g.tail + 1, loss);
     }
 }
 
@@ -613,18 +730,26 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_async_kernel(const Gemm
 // shared-memory traffic falls from 96 KB per k-block (fill, split read, lo write, three MMA reads of hi/lo) to 32 KB.
 // (First version, measured: rows fetched straight from global memory into registers -- correct, but a 16-byte-per-lane
 // row gather costs 32 L1 wavefronts per instruction, as much pipe time as the shared-memory traffic it replaced.)
+#ifndef SZB_TA_DIST
+#define SZB_TA_DIST 2
+#endif
+#ifndef SZB_TA_NBUF
+#define SZB_TA_NBUF 2
+#endif
 template <int BN, int PASSES>
 struct SmemLayoutTa {
     static constexpr int kATile = BM * BK * 4;                       // raw A slab: staged (coalesced cp.async), read once
     static constexpr int kBTile = BN * BK * 4;
     static constexpr int kStageBytes = kATile + kBTile;
-    static constexpr int kDist = 2;
-    static constexpr int kStages = kDist + 2;
-    static constexpr int kLoBytes = PASSES == 3 ? 2 * kBTile : 0;    // lo tiles of B only: A's lo part goes to TMEM
+    static constexpr int kDist = SZB_TA_DIST;                        // k-blocks of cp.async in flight ahead of the tensor core
+    static constexpr int kNBuf = SZB_TA_NBUF;                        // lo tiles of B / TMEM buffers of A: k-blocks the producers may run ahead of the MMAs
+    static constexpr int kStages = kDist + kNBuf;
+    static constexpr int kLoBytes = PASSES == 3 ? kNBuf * kBTile : 0;    // lo tiles of B only: A's lo part goes to TMEM
     static constexpr int kRing = kStages * kStageBytes + kLoBytes;
     static constexpr int kTotal = kRing > 116 * 1024 ? kRing : 116 * 1024;   // > half an SM: one CTA per SM, as the grids assume
     static constexpr int kACols = 32 * (PASSES == 3 ? 2 : 1);            // TMEM columns of one A buffer: [hi 32 | lo 32]
-    static constexpr int kTmemCols = (BN + 2 * kACols) <= 128 ? 128 : ((BN + 2 * kACols) <= 256 ? 256 : 512);
+    static constexpr int kTmemCols = (BN + kNBuf * kACols) <= 128 ? 128 : ((BN + kNBuf * kACols) <= 256 ? 256 : 512);
+    static_assert(BN + kNBuf * kACols <= 512, "tensor memory has 512 columns");
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -644,9 +769,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 template <int BN, int PASSES, int EPI>
-__global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArgs g) {
+__device__ __forceinline__ void gemm_tc_ta_body(const GemmArgs& g, const int bx, const int by, const int bz) {
     using SL = SmemLayoutTa<BN, PASSES>;
-    constexpr int kStages = SL::kStages, kDist = SL::kDist;
+    constexpr int kStages = SL::kStages, kDist = SL::kDist, kNBuf = SL::kNBuf;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint64_t s_full[kStages], s_free[kStages];
     __shared__ uint32_t s_tmem;
@@ -656,8 +781,8 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
     const uint32_t smem_base = smem_u32(tc_smem);
     if ((smem_base & 1023u) != 0) __trap();
     const uint32_t lo_base = smem_base + kStages * SL::kStageBytes;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kb0 = blockIdx.z * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
+    const int m0 = by * BM, n0 = bx * BN;
+    const int kb0 = bz * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
     const int n_kb = (kb1 - kb0 + BK - 1) / BK;
 
     if (warp == 0) {
@@ -714,22 +839,27 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
         const int q = warp & 3, h = warp >> 2;
         const uint32_t a_lane = uint32_t(q * 32) << 16;
         for (int j = 0; j < kDist; ++j) {
+#ifndef SZB_X_NOLOAD
             if (j < n_kb) issue(j);
+#endif
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         for (int kb = 0; kb < n_kb; ++kb) {
-            // MMAs of k-block kb - 2 done => ring stage (kb + kDist) % kStages, lo buffer kb % 2 and TMEM A buffer kb % 2 are free
-            if (kb >= 2) {
-                mbar_wait(&s_free[(kb - 2) % kStages], uint32_t(((kb - 2) / kStages) & 1));
+            // MMAs of k-block kb - kNBuf done => ring stage (kb + kDist) % kStages, lo buffer and TMEM A buffer kb % kNBuf are free
+            if (kb >= kNBuf) {
+                mbar_wait(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+#ifndef SZB_X_NOLOAD
             if (kb + kDist < n_kb) issue(kb + kDist);
+#endif
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kDist) : "memory");   // this thread's chunks of k-block kb have landed
             const uint32_t st = smem_base + (kb % kStages) * SL::kStageBytes;
+#ifndef SZB_X_NOSPLIT
             // ---- B lo split first (own chunks only, no barrier needed), so the barrier below has less to wait for
             if (PASSES == 3) {
-                const uint32_t lo = lo_base + (kb & 1) * SL::kBTile;
+                const uint32_t lo = lo_base + (kb % kNBuf) * SL::kBTile;
 #pragma unroll
                 for (int u = 0; u < kRb; ++u) {
                     const uint32_t off = sw128_off(lr + kRows * u, lc);
@@ -751,7 +881,7 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
                                  : "r"(st + sw128_off(q * 32 + lane, 4 * h + c)));
                     hi[4 * c + 0] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
                 }
-                const uint32_t abuf = tmem_a + a_lane + uint32_t((kb & 1) * SL::kACols + h * 16);
+                const uint32_t abuf = tmem_a + a_lane + uint32_t((kb % kNBuf) * SL::kACols + h * 16);
                 tmem_st16(abuf, hi);                     // kind::tf32 reads the upper 19 bits: the raw word is the hi operand
                 if (PASSES == 3) {
 #pragma unroll
@@ -760,6 +890,7 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&s_full[kb % kStages]);
@@ -773,13 +904,16 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
             mbar_wait(&s_full[kb % kStages], uint32_t((kb / kStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t db_hi = make_desc_k_sw128(smem_base + (kb % kStages) * SL::kStageBytes + SL::kATile);
-            const uint64_t db_lo = make_desc_k_sw128(lo_base + (kb & 1) * SL::kBTile);
-            const uint32_t a_hi = tmem_a + uint32_t((kb & 1) * SL::kACols), a_lo = a_hi + 32;
+            const uint64_t db_lo = make_desc_k_sw128(lo_base + (kb % kNBuf) * SL::kBTile);
+            const uint32_t a_hi = tmem_a + uint32_t((kb % kNBuf) * SL::kACols), a_lo = a_hi + 32;
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
                 const uint64_t adv = uint64_t((k * UK * 4) >> 4);
                 const uint32_t acol = uint32_t(k * UK);
                 const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+#ifdef SZB_X_NOMMA
+                if (kb > 0) continue;      // experiment: one k-block of MMAs only (the accumulator is defined), then bare commits
+#endif
                 if (PASSES == 3) {
                     umma_tf32_ts(tmem_d, a_lo + acol, db_hi + adv, idesc, acc0);
                     umma_tf32_ts(tmem_d, a_hi + acol, db_lo + adv, idesc, 1u);
@@ -798,14 +932,48 @@ __global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArg
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         SZB_TRACE(4);
-        tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
-                                        reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
+        if (EPI == TC_SOFTMAX_CE) {      // the whole row of logits sits in this tile (launcher: N <= BN, one column of tiles)
+            if (warp < 4) tc_epilogue_softmax(g, tmem_d, m0, n_kb > 0, reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
+        } else {
+            tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
+                                            reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     SZB_TRACE(5);
     __syncthreads();
     SZB_TRACE(6);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(SL::kTmemCols) : "memory");
+}
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_kernel(const GemmArgs g) {
+    gemm_tc_ta_body<BN, PASSES, EPI>(g, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several independent products in ONE launch (the three weight-gradient GEMMs of a training step: each depends only on the
+// activations and deltas, none on another).  As three launches each of them was cut into ~148 short K ranges to fill the SMs
+// -- dW3 into 49 ranges of three k-blocks -- and paid set-up, pipeline fill and a full tile of vector reductions per range;
+// one launch shares the 148 SMs among all tiles, so a CTA walks a K range several times longer and the reduction traffic
+// falls by the same factor.  CTA b serves problem p with first[p] <= b < first[p + 1]; inside a problem the CTAs are ordered
+// (column tile, row tile, K range) like the grid of the single-problem kernel.
+constexpr int kMaxGroup = 3;
+struct GroupArgs {
+    GemmArgs g[kMaxGroup];
+    int first[kMaxGroup + 1];
+    int tiles_n[kMaxGroup], tiles_m[kMaxGroup];
+    int count;
+};
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kThreadsAsync) gemm_tc_ta_group_kernel(const __grid_constant__ GroupArgs ga) {
+    const int b = blockIdx.x;
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGroup; ++i)
+        if (i < ga.count && b >= ga.first[i]) p = i;
+    const int local = b - ga.first[p];
+    const int tn = ga.tiles_n[p], tm = ga.tiles_m[p];
+    gemm_tc_ta_body<BN, PASSES, EPI>(ga.g[p], local % tn, (local / tn) % tm, local / (tn * tm));
 }
 
 template <int BN, int PASSES, int EPI>
@@ -844,6 +1012,74 @@ szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
     }
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    return SZB_OK;
+}
+
+inline bool gemm_operands_aligned(const GemmArgs& g) {
+    return g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
+}
+
+// Layer 3 of a training step with softmax / cross-entropy in the epilogue (tc_epilogue_softmax).  Needs the whole row of
+// logits in one 128-column tile and the TMEM-A kernel; *done = false (nothing launched) otherwise: the caller then runs the
+// plain bias epilogue followed by softmax_train_kernel.
+template <int PASSES>
+szb_status launch_gemm_tc_softmax(szb_ctx* ctx, GemmArgs g, bool* done) {
+    constexpr int BN = 128;
+    *done = false;
+    if (g.M <= 0 || g.N <= 0 || g.N > BN || g.K <= 0 || !ctx->gemm_ta || !gemm_operands_aligned(g)) return SZB_OK;
+    using SLT = SmemLayoutTa<BN, PASSES>;
+    g.k_chunk = ((g.K + BK - 1) / BK) * BK;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_ta_kernel<BN, PASSES, TC_SOFTMAX_CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLT::kTotal));
+        attr_set[ctx->device & 63] = true;
+    }
+    SZB_CUDA(launch_pdl(ctx, gemm_tc_ta_kernel<BN, PASSES, TC_SOFTMAX_CE>, dim3(1, (g.M + BM - 1) / BM, 1), dim3(kThreadsAsync), size_t(SLT::kTotal), g));
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    *done = true;
+    return SZB_OK;
+}
+
+// The weight-gradient GEMMs of a step (split-K, vector reductions into the gradient vector) as one launch of
+// gemm_tc_ta_group_kernel.  The K ranges are sized so that all tiles of all problems together fill the SMs once.
+// *done = false (nothing launched) when an operand is not 16-byte aligned or the TMEM-A kernel is switched off.
+template <int PASSES>
+szb_status launch_gemm_tc_group(szb_ctx* ctx, const GemmArgs* gs, int count, bool* done) {
+    constexpr int BN = 128;
+    *done = false;
+    if (count < 1 || count > kMaxGroup || !ctx->gemm_ta) return SZB_OK;
+    GroupArgs ga{};
+    int total_tiles = 0;
+    for (int p = 0; p < count; ++p) {
+        if (gs[p].M <= 0 || gs[p].N <= 0 || gs[p].K <= 0 || !gemm_operands_aligned(gs[p])) return SZB_OK;
+        ga.g[p] = gs[p];
+        ga.tiles_n[p] = (gs[p].N + BN - 1) / BN;
+        ga.tiles_m[p] = (gs[p].M + BM - 1) / BM;
+        total_tiles += ga.tiles_n[p] * ga.tiles_m[p];
+    }
+    const int split = std::max(1, ctx->sm_count / std::max(1, total_tiles));
+    int ctas = 0;
+    for (int p = 0; p < count; ++p) {
+        const int kb_total = (gs[p].K + BK - 1) / BK;
+        const int sp = std::max(1, std::min(split, kb_total));
+        ga.g[p].k_chunk = ((kb_total + sp - 1) / sp) * BK;
+        const int nz = (gs[p].K + ga.g[p].k_chunk - 1) / ga.g[p].k_chunk;      // every K range is non-empty
+        ga.first[p] = ctas;
+        ctas += ga.tiles_n[p] * ga.tiles_m[p] * nz;
+    }
+    for (int p = count; p <= kMaxGroup; ++p) ga.first[p] = ctas;
+    ga.count = count;
+    using SLT = SmemLayoutTa<BN, PASSES>;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_ta_group_kernel<BN, PASSES, TC_ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLT::kTotal));
+        attr_set[ctx->device & 63] = true;
+    }
+    SZB_CUDA(launch_pdl(ctx, gemm_tc_ta_group_kernel<BN, PASSES, TC_ATOMIC>, dim3(ctas), dim3(kThreadsAsync), size_t(SLT::kTotal), ga));
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    *done = true;
     return SZB_OK;
 }
 

@@ -1,0 +1,370 @@
+// Third generation of the dense-layer GEMM (same operand form and epilogues as gemm_tc.cuh: C[M,N] (+)= A[M,K] * B[N,K]^T, both
+// operands K-contiguous FP32, 3xTF32 split, accumulator and the A operand in tensor memory):
+//
+//   * operands travel global -> shared memory by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps, completion on an
+//     mbarrier with expect_tx; rows / columns past the matrix edge are zero-filled by the unit) -- one thread issues two bulk
+//     copies per k-block where 256 threads issued eight 16-byte cp.async each and then waited on their own copy groups;
+//   * the work between "tile landed" and "MMAs may start" is split over two producer groups that run concurrently:
+//     warps 0-7 move the A slab into tensor memory (own row read back from the swizzled tile, lo = x - trunc(x), two
+//     tcgen05.st), warps 8-15 write the lo tile of B.  In gemm_tc_ta_kernel the same eight warps did both in sequence,
+//     separated by a block barrier (the copies of a row were issued by other threads); with TMA the mbarrier makes the whole
+//     tile visible, so the barrier is gone too;
+//   * one mbarrier arrival per warp (after __syncwarp) instead of one per thread: 16 arrivals per k-block instead of 256;
+//   * all sixteen producer warps run the epilogue (a TMEM lane quarter x a quarter of the columns each).
+//
+// Why (measured on B200 with tools/micro/gemm_step_bench.cu experiments, profiles/r02_gemm_kloop_experiments.txt): the K
+// loop of gemm_tc_ta_kernel was PRODUCER-bound -- fwd2 (16 k-blocks) needs 10.2 us with the MMAs removed, 7.9 us with only
+// the MMAs, 5.9 us with only the copies, 11.1 us as a whole; deeper cp.async look-ahead or more lo / TMEM buffers change
+// nothing.  tools/micro/mma_rate.cu: a 128 x 128 x 8 TF32 MMA issues at its 64-clock floor, a 128 x 64 x 8 one at 55 clocks
+// (floor 32), and a commit + wait per 12 MMAs costs ~20 clocks per MMA.
+#pragma once
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "gemm_tc.cuh"
+
+namespace szb {
+namespace tc {
+
+#ifndef SZB_TMA_NBUF
+#define SZB_TMA_NBUF 2
+#endif
+#ifndef SZB_TMA_STAGES
+#define SZB_TMA_STAGES 4
+#endif
+
+constexpr int kTmaProducerWarps = 16;                         // 0-7: A -> tensor memory, 8-15: lo tile of B
+constexpr int kTmaThreads = (kTmaProducerWarps + 2) * 32;     // + warp 16 (MMA issuer) + warp 17 (TMA issuer)
+
+template <int BN, int PASSES>
+struct SmemLayoutTma {
+    static constexpr int kATile = BM * BK * 4;
+    static constexpr int kBTile = BN * BK * 4;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kNBuf = SZB_TMA_NBUF;                   // lo tiles of B / TMEM buffers of A
+    static constexpr int kStages = SZB_TMA_STAGES;               // raw tiles in flight or in use
+    static constexpr int kLoBytes = PASSES == 3 ? kNBuf * kBTile : 0;
+    static constexpr int kRing = kStages * kStageBytes + kLoBytes;
+    static constexpr int kTotal = kRing > 116 * 1024 ? kRing : 116 * 1024;   // > half an SM: one CTA per SM (TMEM, PDL: see gemm_tc.cuh)
+    static constexpr int kACols = 32 * (PASSES == 3 ? 2 : 1);
+    static constexpr int kTmemCols = (BN + kNBuf * kACols) <= 128 ? 128 : ((BN + kNBuf * kACols) <= 256 ? 256 : 512);
+    static_assert(kStages >= kNBuf, "a raw tile stays until its MMAs are done");
+    static_assert(BN + kNBuf * kACols <= 512, "tensor memory has 512 columns");
+    static_assert(kTotal >= kTmaProducerWarps * kEpiWarpBytes, "the epilogue stages its tiles in the ring");
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// box (c0 .. c0 + 31 along K, r0 .. r0 + rows - 1) of a [rows][K] FP32 matrix -> a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int r0, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(r0), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int BN, int PASSES, int EPI>
+__device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorMap* tmA, const CUtensorMap* tmB, const int bx, const int by,
+                                              const int bz) {
+    using SL = SmemLayoutTma<BN, PASSES>;
+    constexpr int kStages = SL::kStages, kNBuf = SL::kNBuf;
+    constexpr int kFullCount = PASSES == 3 ? kTmaProducerWarps : kTmaProducerWarps / 2;     // one arrival per working warp
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ uint64_t s_loaded[kStages], s_full[kStages], s_free[kStages], s_done;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SZB_TRACE(0);
+    const uint32_t smem_base = smem_u32(tc_smem);
+    if ((smem_base & 1023u) != 0) __trap();
+    const uint32_t lo_base = smem_base + kStages * SL::kStageBytes;
+    const int m0 = by * BM, n0 = bx * BN;
+    const int kb0 = bz * g.k_chunk, kb1 = min(g.K, kb0 + g.k_chunk);
+    const int n_kb = (kb1 - kb0 + BK - 1) / BK;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(SL::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_loaded[s], 1);
+            mbar_init(&s_full[s], kFullCount);
+            mbar_init(&s_free[s], 1);
+        }
+        mbar_init(&s_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem;                      // columns [0, BN): accumulator
+    const uint32_t tmem_a = s_tmem + BN;                 // then kNBuf A buffers of kACols columns
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    pdl_launch_dependents();                             // only with this CTA's tensor memory allocated (see gemm_tc_ta_body)
+    pdl_wait();
+    SZB_TRACE(1);
+
+    if (warp == kTmaProducerWarps + 1) {
+        // ------------------------------------------------ TMA issuer -----------------------------------------------
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kStages;
+                if (kb >= kStages) mbar_wait(&s_free[s], uint32_t((kb / kStages - 1) & 1));      // MMAs of k-block kb - kStages are done
+                const uint32_t st = smem_base + s * SL::kStageBytes;
+                mbar_expect_tx(&s_loaded[s], uint32_t(SL::kStageBytes));
+                tma_load_2d(st, tmA, kb0 + kb * BK, m0, &s_loaded[s]);
+                tma_load_2d(st + SL::kATile, tmB, kb0 + kb * BK, n0, &s_loaded[s]);
+            }
+        }
+    } else if (warp == kTmaProducerWarps) {
+        // ------------------------------------------------ MMA issuer -----------------------------------------------
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(&s_full[s], uint32_t((kb / kStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t db_hi = make_desc_k_sw128(smem_base + s * SL::kStageBytes + SL::kATile);
+                const uint64_t db_lo = make_desc_k_sw128(lo_base + (kb % kNBuf) * SL::kBTile);
+                const uint32_t a_hi = tmem_a + uint32_t((kb % kNBuf) * SL::kACols), a_lo = a_hi + 32;
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                    const uint64_t adv = uint64_t((k * UK * 4) >> 4);
+                    const uint32_t acol = uint32_t(k * UK);
+                    const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+                    if (PASSES == 3) {
+                        umma_tf32_ts(tmem_d, a_lo + acol, db_hi + adv, idesc, acc0);
+                        umma_tf32_ts(tmem_d, a_hi + acol, db_lo + adv, idesc, 1u);
+                        umma_tf32_ts(tmem_d, a_hi + acol, db_hi + adv, idesc, 1u);
+                    } else {
+                        umma_tf32_ts(tmem_d, a_hi + acol, db_hi + adv, idesc, acc0);
+                    }
+                }
+                umma_commit(&s_free[s]);
+            }
+            // End of the tile on a barrier of its own: warps that do not walk the K loop (8-15 in single-pass mode) cannot wait
+            // for "completion number n_kb / kStages" of a ring barrier by parity -- an mbarrier still in its first phase
+            // answers a wait for the odd parity at once.
+            if (n_kb > 0) umma_commit(&s_done);
+        }
+    } else if (warp < 8) {
+        // ------------------------------------- A slab -> tensor memory (warps 0-7) --------------------------------
+        // thread <-> row 32 (warp & 3) + lane of the tile (its TMEM lane), 16-byte chunks [4 h, 4 h + 4) of the k-block
+        const int q = warp & 3, h = warp >> 2;
+        const uint32_t a_lane = uint32_t(q * 32) << 16;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % kStages;
+            if (kb >= kNBuf) {          // MMAs of k-block kb - kNBuf done: TMEM A buffer kb % kNBuf is free
+                mbar_wait(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            mbar_wait(&s_loaded[s], uint32_t((kb / kStages) & 1));
+            const uint32_t st = smem_base + s * SL::kStageBytes;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(st + sw128_off(q * 32 + lane, 4 * h + c)));
+                hi[4 * c + 0] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+            }
+            const uint32_t abuf = tmem_a + a_lane + uint32_t((kb % kNBuf) * SL::kACols + h * 16);
+            tmem_st16(abuf, hi);                     // kind::tf32 reads the upper 19 bits: the raw word is the hi operand
+            if (PASSES == 3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) lo[j] = hi[j] - tf32_trunc(hi[j]);
+                tmem_st16(abuf + 32, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            if (kb == 0) SZB_TRACE(2);
+        }
+        SZB_TRACE(3);
+    } else if (PASSES == 3) {
+        // --------------------------------------- lo tile of B (warps 8-15) ----------------------------------------
+        // thread <-> 16-byte chunk (t & 7) of rows (t >> 3) + 32 u; the raw tile itself is the hi operand
+        const int t = tid - 256, lr = t >> 3, lc = t & 7;
+        constexpr int kRb = BN / 32;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % kStages;
+            if (kb >= kNBuf) mbar_wait(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));   // lo buffer kb % kNBuf is free
+            mbar_wait(&s_loaded[s], uint32_t((kb / kStages) & 1));
+            const uint32_t src = smem_base + s * SL::kStageBytes + SL::kATile;
+            const uint32_t dst = lo_base + (kb % kNBuf) * SL::kBTile;
+            float4 v[kRb];
+#pragma unroll
+            for (int u = 0; u < kRb; ++u)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                             : "r"(src + sw128_off(lr + 32 * u, lc)));
+#pragma unroll
+            for (int u = 0; u < kRb; ++u)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + sw128_off(lr + 32 * u, lc)), "f"(v[u].x - tf32_trunc(v[u].x)),
+                             "f"(v[u].y - tf32_trunc(v[u].y)), "f"(v[u].z - tf32_trunc(v[u].z)), "f"(v[u].w - tf32_trunc(v[u].w))
+                             : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+        }
+    }
+    if (warp < kTmaProducerWarps) {
+        if (n_kb > 0) mbar_wait(&s_done, 0u);                                       // every MMA of the tile has completed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        SZB_TRACE(4);
+        // every MMA has completed, every bulk copy was consumed by one: the ring is free to stage the output tile.
+        // A warp takes its TMEM lane quarter (warp & 3) x 32 columns (warp >> 2).
+        constexpr int kEpiWarps = (BN / 32) * 4;
+        if (warp < kEpiWarps)
+            tc_epilogue_staged<32, EPI>(g, tmem_d + uint32_t((warp >> 2) * 32), m0, n0 + (warp >> 2) * 32, n_kb > 0,
+                                        reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    SZB_TRACE(5);
+    __syncthreads();
+    SZB_TRACE(6);
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(SL::kTmemCols) : "memory");
+}
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kTmaThreads) gemm_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB) {
+    gemm_tma_body<BN, PASSES, EPI>(g, &tmA, &tmB, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several independent products in one launch (see gemm_tc_ta_group_kernel).
+struct GroupArgsTma {
+    GemmArgs g[kMaxGroup];
+    CUtensorMap tmA[kMaxGroup], tmB[kMaxGroup];
+    int first[kMaxGroup + 1];
+    int tiles_n[kMaxGroup], tiles_m[kMaxGroup];
+    int count;
+};
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kTmaThreads) gemm_tma_group_kernel(const __grid_constant__ GroupArgsTma ga) {
+    const int b = blockIdx.x;
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGroup; ++i)
+        if (i < ga.count && b >= ga.first[i]) p = i;
+    const int local = b - ga.first[p];
+    const int tn = ga.tiles_n[p], tm = ga.tiles_m[p];
+    gemm_tma_body<BN, PASSES, EPI>(ga.g[p], &ga.tmA[p], &ga.tmB[p], local % tn, (local / tn) % tm, local / (tn * tm));
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver (no link-time dependency on libcuda: cudaGetDriverEntryPoint).  A map
+// depends only on (base, rows, cols, row stride, box rows); the buffers of a net are stable, so the few maps a step needs are
+// encoded once and found again by a linear search.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct TensorMapKey {
+    const void* base; int rows, cols, ld, box_rows;
+    bool operator==(const TensorMapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+// [rows][cols] FP32, row stride ld floats (16-byte multiple), boxes of box_rows x 32 floats, SWIZZLE_128B.  false: not encodable.
+inline bool tensor_map_for(const float* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::vector<std::pair<TensorMapKey, CUtensorMap>> cache;
+    const TensorMapKey key{base, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : cache)
+        if (e.first == key) { *out = e.second; return true; }
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+    const cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm;
+    if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() >= 256) cache.erase(cache.begin(), cache.begin() + 128);
+    cache.emplace_back(key, tm);
+    *out = tm;
+    return true;
+}
+
+// *done = false (nothing launched): operands not 16-byte aligned, TMA switched off, or no driver entry point -- the caller
+// falls back to launch_gemm_tc.
+template <int BN, int PASSES, int EPI>
+szb_status launch_gemm_tma(szb_ctx* ctx, GemmArgs g, int split_k, bool* done) {
+    *done = false;
+    if (g.M <= 0 || g.N <= 0) { *done = true; return SZB_OK; }
+    if (!ctx->gemm_tma || g.K <= 0 || !gemm_operands_aligned(g)) return SZB_OK;
+    CUtensorMap tmA, tmB;
+    if (!tensor_map_for(g.A, g.M, g.K, g.lda, BM, &tmA) || !tensor_map_for(g.B, g.N, g.K, g.ldb, BN, &tmB)) return SZB_OK;
+    using SL = SmemLayoutTma<BN, PASSES>;
+    const int kb_total = (g.K + BK - 1) / BK;
+    split_k = EPI == TC_ATOMIC ? std::max(1, std::min(split_k, kb_total)) : 1;
+    g.k_chunk = ((kb_total + split_k - 1) / split_k) * BK;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.K + g.k_chunk - 1) / g.k_chunk);
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        attr_set[ctx->device & 63] = true;
+    }
+    SZB_CUDA(launch_pdl(ctx, gemm_tma_kernel<BN, PASSES, EPI>, grid, dim3(kTmaThreads), size_t(SL::kTotal), g, tmA, tmB));
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    *done = true;
+    return SZB_OK;
+}
+
+template <int PASSES>
+szb_status launch_gemm_tma_group(szb_ctx* ctx, const GemmArgs* gs, int count, bool* done) {
+    constexpr int BN = 128;
+    *done = false;
+    if (count < 1 || count > kMaxGroup || !ctx->gemm_tma) return SZB_OK;
+    GroupArgsTma ga{};
+    int total_tiles = 0;
+    for (int p = 0; p < count; ++p) {
+        if (gs[p].M <= 0 || gs[p].N <= 0 || gs[p].K <= 0 || !gemm_operands_aligned(gs[p])) return SZB_OK;
+        if (!tensor_map_for(gs[p].A, gs[p].M, gs[p].K, gs[p].lda, BM, &ga.tmA[p]) || !tensor_map_for(gs[p].B, gs[p].N, gs[p].K, gs[p].ldb, BN, &ga.tmB[p]))
+            return SZB_OK;
+        ga.g[p] = gs[p];
+        ga.tiles_n[p] = (gs[p].N + BN - 1) / BN;
+        ga.tiles_m[p] = (gs[p].M + BM - 1) / BM;
+        total_tiles += ga.tiles_n[p] * ga.tiles_m[p];
+    }
+    const int split = std::max(1, ctx->sm_count / std::max(1, total_tiles));
+    int ctas = 0;
+    for (int p = 0; p < count; ++p) {
+        const int kb_total = (gs[p].K + BK - 1) / BK;
+        const int sp = std::max(1, std::min(split, kb_total));
+        ga.g[p].k_chunk = ((kb_total + sp - 1) / sp) * BK;
+        const int nz = (gs[p].K + ga.g[p].k_chunk - 1) / ga.g[p].k_chunk;      // every K range is non-empty
+        ga.first[p] = ctas;
+        ctas += ga.tiles_n[p] * ga.tiles_m[p] * nz;
+    }
+    for (int p = count; p <= kMaxGroup; ++p) ga.first[p] = ctas;
+    ga.count = count;
+    using SL = SmemLayoutTma<BN, PASSES>;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tma_group_kernel<BN, PASSES, TC_ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        attr_set[ctx->device & 63] = true;
+    }
+    SZB_CUDA(launch_pdl(ctx, gemm_tma_group_kernel<BN, PASSES, TC_ATOMIC>, dim3(ctas), dim3(kTmaThreads), size_t(SL::kTotal), ga));
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    *done = true;
+    return SZB_OK;
+}
+
+}  // namespace tc
+}  // namespace szb

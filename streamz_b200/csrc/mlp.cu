@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 #include "mlp.cuh"
 
 namespace szb {
@@ -296,61 +297,75 @@ __global__ void colsum_kernel(const float* __restrict__ D, int rows, int cols, i
 }
 
 // Gather rows perm[s..s+B) of feats, apply input dropout (lib.rs:119-129, no rescale), flag windows left all-zero
-// (lib.rs:607-609).  One block = 32 batch rows, one warp per row (4 rows per warp); the transposed copy the weight-gradient
-// GEMM reads is staged in shared memory ([n_in][33] floats, when it fits) and leaves as 128-byte row segments.
-__global__ void prep_batch_kernel(const float* __restrict__ feats, const uint32_t* __restrict__ labels_all,
-                                  const uint32_t* __restrict__ perm, int B, int n_in, const uint8_t* __restrict__ keep,
-                                  int keep_by_row /* keep indexed by window id (1) or by batch row (0) */, float prob,
-                                  unsigned long long key, float* __restrict__ xb, float* __restrict__ xbT, uint32_t* __restrict__ lab,
-                                  uint8_t* __restrict__ valid, float* __restrict__ h1T, int h1, float* __restrict__ h2T, int h2,
-                                  int use_tile, const StepParams* __restrict__ sp) {
-    extern __shared__ float prep_tile[];   // [n_in][33] when use_tile
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
-    if (sp) {                              // captured step: position in the shuffled order and dropout key come from device memory
-        perm += sp->cursor;
-        key = sp->key;
-    }
+// (lib.rs:607-609).  One block = 32 batch rows, a warp per row (or several rows per warp); the transposed copy the
+// weight-gradient GEMM reads is staged in shared memory ([n_in][33] floats, when it fits) and leaves as 128-byte row segments.
+// The body is shared by prep_batch_kernel and by the extra CTAs of sgd_fused_kernel that prepare the NEXT batch.
+struct PrepArgs {
+    const float* feats; const uint32_t* labels_all; const uint32_t* perm;
+    int B, n_in;
+    const uint8_t* keep; int keep_by_row;   // keep indexed by window id (1) or by batch row (0)
+    float prob; unsigned long long key;
+    float* xb; float* xbT; uint32_t* lab; uint8_t* valid;
+    float* h1T; int h1; float* h2T; int h2;
+    int use_tile;
+};
+
+__device__ __forceinline__ void prep_batch_block(const PrepArgs& a, const int block, const uint32_t* __restrict__ perm,
+                                                 const unsigned long long key, float* prep_tile /* [n_in][33] when use_tile */) {
+    const int B = a.B, n_in = a.n_in;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int row0 = blockIdx.x * 32;
+    const int row0 = block * 32;
     for (int r = warp; r < 32; r += nw) {
         const int row = row0 + r;
         if (row >= B) break;
         const uint32_t w = perm ? perm[row] : uint32_t(row);
         bool any = false;
         for (int i = lane; i < n_in; i += 32) {
-            float v = feats[size_t(w) * n_in + i];
-            if (keep) {
-                if (!keep[size_t(keep_by_row ? w : uint32_t(row)) * n_in + i]) v = 0.f;
-            } else if (prob > 0.f) {
-                if (!dropout_keep(key, w, uint32_t(i), prob)) v = 0.f;
+            float v = a.feats[size_t(w) * n_in + i];
+            if (a.keep) {
+                if (!a.keep[size_t(a.keep_by_row ? w : uint32_t(row)) * n_in + i]) v = 0.f;
+            } else if (a.prob > 0.f) {
+                if (!dropout_keep(key, w, uint32_t(i), a.prob)) v = 0.f;
             }
-            xb[size_t(row) * n_in + i] = v;
-            if (xbT) {
-                if (use_tile) prep_tile[i * 33 + r] = v;
-                else xbT[size_t(i) * B + row] = v;
+            a.xb[size_t(row) * n_in + i] = v;
+            if (a.xbT) {
+                if (a.use_tile) prep_tile[i * 33 + r] = v;
+                else a.xbT[size_t(i) * B + row] = v;
             }
             any |= (v != 0.f);
         }
         any = __any_sync(0xffffffffu, any);
         if (lane == 0) {
-            valid[row] = any ? 1 : 0;
-            if (lab) lab[row] = labels_all ? labels_all[w] : 0xffffffffu;
+            a.valid[row] = any ? 1 : 0;
+            if (a.lab) a.lab[row] = a.labels_all ? a.labels_all[w] : 0xffffffffu;
         }
     }
-    if (!xbT) return;
+    if (!a.xbT) return;
     const int nrows = min(32, B - row0);
-    if (use_tile) {
+    if (a.use_tile) {
         __syncthreads();
         for (int i = warp; i < n_in; i += nw)
-            if (lane < nrows) xbT[size_t(i) * B + row0 + lane] = prep_tile[i * 33 + lane];
+            if (lane < nrows) a.xbT[size_t(i) * B + row0 + lane] = prep_tile[i * 33 + lane];
     }
     // row of ones under each transposed activation: the weight-gradient GEMM then yields the bias gradient
     if (warp == 0 && lane < nrows) {
-        xbT[size_t(n_in) * B + row0 + lane] = 1.f;
-        h1T[size_t(h1) * B + row0 + lane] = 1.f;
-        h2T[size_t(h2) * B + row0 + lane] = 1.f;
+        a.xbT[size_t(n_in) * B + row0 + lane] = 1.f;
+        a.h1T[size_t(a.h1) * B + row0 + lane] = 1.f;
+        a.h2T[size_t(a.h2) * B + row0 + lane] = 1.f;
     }
+}
+
+__global__ void prep_batch_kernel(const __grid_constant__ PrepArgs a, const StepParams* __restrict__ sp) {
+    extern __shared__ float prep_tile[];   // [n_in][33] when use_tile
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const uint32_t* perm = a.perm;
+    unsigned long long key = a.key;
+    if (sp) {                              // captured step: position in the shuffled order and dropout key come from device memory
+        perm += sp->cursor;
+        key = sp->key;
+    }
+    prep_batch_block(a, blockIdx.x, perm, key, prep_tile);
 }
 
 // theta -= (lr / n_used) * g   (lib.rs:1047-1059); n_used comes from the (all-reduced) gradient tail.
@@ -397,6 +412,7 @@ struct P2pArgs {
     int rank, world;
     uint32_t step;
     uint32_t n4, slice_g;                    // 16-byte groups in V, groups per slice
+    int nblk;                                // CTAs taking part in the exchange: blocks [0, nblk) of the grid (0 = the whole grid)
 };
 
 __device__ __forceinline__ void p2p_wait_flags(const uint32_t* f, int world, uint32_t step) {
@@ -428,7 +444,7 @@ __device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* coun
     if (threadIdx.x == 0) {
         __threadfence_system();
         const unsigned int ticket = atomicAdd(counter, 1u);
-        s_last = ticket == gridDim.x - 1;
+        s_last = ticket == (a.nblk ? unsigned(a.nblk) : gridDim.x) - 1;
         if (s_last) *counter = 0u;                         // every CTA has arrived; the next step finds it zero
     }
     __syncthreads();
@@ -451,7 +467,7 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
     const int me = a.rank, W = a.world;
     const bool tr = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long t_prev = tr ? p2p_now() : 0ull;
-    const size_t nthreads = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nthreads = size_t(a.nblk ? unsigned(a.nblk) : gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const float4* G4 = reinterpret_cast<const float4*>(G);
     if (a.one_shot) {
         // ONE-SHOT: the whole vector goes to every peer (W - 1 posted stores per 16-byte group), one flag round, and every rank
@@ -541,10 +557,19 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
                                                         int h1, int h2, int n_out, size_t off_b1, size_t off_w2, size_t off_b2,
                                                         size_t off_w3, size_t off_b3, size_t off_wt2, size_t off_wt3, size_t np, int parity,
                                                         float lr, double* __restrict__ stats, const __grid_constant__ P2pArgs a,
-                                                        StepParams* __restrict__ sp, int advance) {
+                                                        StepParams* __restrict__ sp, int advance, const __grid_constant__ PrepArgs next,
+                                                        const int n_upd /* blocks [0, n_upd) update, the rest prepare the next batch */) {
     __shared__ float tile[32][33];
+    extern __shared__ float next_tile[];   // [n_in][33] of a batch-preparing block
     tc::pdl_launch_dependents();
     tc::pdl_wait();
+    if (int(blockIdx.x) >= n_upd) {
+        // The next step's batch: gathered, dropped out and transposed while the other blocks exchange and apply this step's
+        // gradient.  Everything that read the batch buffers (the step's GEMMs) completed before griddepcontrol.wait returned,
+        // and nothing in the update touches them.
+        prep_batch_block(next, int(blockIdx.x) - n_upd, next.perm, next.key, next_tile);
+        return;
+    }
     if (sp) {                              // captured step (CUDA graph): learning rate from device memory; move on to the next batch
         lr = sp->lr;                       // (the next step's batch kernel reads the position only after this grid has completed)
         if (blockIdx.x == 0 && threadIdx.x == 0) sp->cursor += uint32_t(advance);
@@ -567,7 +592,7 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     const int t1 = ((n_in + 31) / 32) * ((h1 + 31) / 32), t2 = ((h1 + 31) / 32) * ((h2 + 31) / 32),
               t3 = ((h2 + 31) / 32) * ((n_out + 31) / 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = blockIdx.x; t < t1 + t2 + t3; t += gridDim.x) {
+    for (int t = blockIdx.x; t < t1 + t2 + t3; t += n_upd) {
         int K, N, tt;
         size_t off_w, off_wt;
         if (t < t1) { K = n_in; N = h1; tt = t; off_w = 0; off_wt = 0; }
@@ -597,8 +622,8 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
     const size_t nb = size_t(h1) + h2 + n_out;
     const int nblk_tiles = t1 + t2 + t3;
     // biases: spread over the blocks starting behind the last tile's block
-    const size_t bt = size_t((blockIdx.x + gridDim.x - (nblk_tiles % gridDim.x)) % gridDim.x) * blockDim.x + threadIdx.x;
-    for (size_t i = bt; i < nb; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t bt = size_t((int(blockIdx.x) + n_upd - (nblk_tiles % n_upd)) % n_upd) * blockDim.x + threadIdx.x;
+    for (size_t i = bt; i < nb; i += size_t(n_upd) * blockDim.x) {
         const size_t idx = i < size_t(h1) ? off_b1 + i : (i < size_t(h1) + h2 ? off_b2 + (i - h1) : off_b3 + (i - h1 - h2));
         P[idx] -= grad_at(idx) * scale;
         G[idx] = 0.f;
@@ -750,13 +775,33 @@ static szb_status gemm_tc(szb_net* net, tc::GemmArgs g, int split_k = 1) {
     // 128 x 64 tiles double the CTA count
     const int tiles128 = ((g.M + 127) / 128) * ((g.N + 127) / 128) * std::max(1, split_k);
     const bool narrow = tiles128 * 10 < net->ctx->sm_count * 7 && g.N > 64;
+    bool done = false;
+    if (net->precision == 2) {
+        if (narrow) SZB_TRY((tc::launch_gemm_tma<64, 1, EPI>(net->ctx, g, split_k, &done)));
+        else SZB_TRY((tc::launch_gemm_tma<128, 1, EPI>(net->ctx, g, split_k, &done)));
+    } else {
+        if (narrow) SZB_TRY((tc::launch_gemm_tma<64, 3, EPI>(net->ctx, g, split_k, &done)));
+        else SZB_TRY((tc::launch_gemm_tma<128, 3, EPI>(net->ctx, g, split_k, &done)));
+    }
+    if (done) return SZB_OK;
     if (net->precision == 2)
         return narrow ? tc::launch_gemm_tc<64, 1, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 1, EPI>(net->ctx, g, split_k);
     return narrow ? tc::launch_gemm_tc<64, 3, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 3, EPI>(net->ctx, g, split_k);
 }
 
-// forward for rows already in d_x (device); leaves logits in a_z; activations in a_h1 / a_h2
-static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool training = false) {
+// What the layer-3 epilogue of a training step needs to finish the forward pass itself (tc_epilogue_softmax)
+struct SoftmaxCe {
+    const uint32_t* labels; const float* target_vec; const uint8_t* valid;
+    float* tail;     // [n_used, loss] block of the gradient vector this step accumulates into
+    float* zT;       // transposed delta3 [n_out][B]
+};
+
+// forward for rows already in d_x (device); leaves logits in a_z; activations in a_h1 / a_h2.
+// With `ce` (training, tensor-core path) layer 3 may run softmax / cross-entropy in its epilogue: *ce_done then says that a_z
+// already holds delta3 (and ce->zT its transpose) and the loss / count are in ce->tail.
+static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool training = false, const SoftmaxCe* ce = nullptr,
+                               bool* ce_done = nullptr) {
+    if (ce_done) *ce_done = false;
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
     if (net->precision != 0) {
@@ -774,6 +819,13 @@ static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool train
         g = tc::GemmArgs{};
         g.A = net->a_h2.as<float>(); g.lda = H2; g.B = WT + net->off_wt3(); g.ldb = H2; g.C = net->a_z.as<float>(); g.ldc = C;
         g.bias = P + net->off_b3(); g.M = B; g.N = C; g.K = H2;
+        if (ce && ce_done && C <= 128) {
+            tc::GemmArgs gs = g;
+            gs.CT = ce->zT; gs.ldct = B; gs.labels = ce->labels; gs.target_vec = ce->target_vec; gs.valid = ce->valid; gs.tail = ce->tail;
+            if (net->precision == 2) SZB_TRY(tc::launch_gemm_tc_softmax<1>(net->ctx, gs, ce_done));
+            else SZB_TRY(tc::launch_gemm_tc_softmax<3>(net->ctx, gs, ce_done));
+            if (*ce_done) return SZB_OK;
+        }
         SZB_TRY(gemm_tc<tc::TC_BIAS>(net, g));
         return SZB_OK;
     }
@@ -837,7 +889,11 @@ szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n);  // comm.cu
 szb_status comm_allreduce_overlapped(szb_ctx* ctx, float* buf, size_t n);
 szb_status comm_join(szb_ctx* ctx);
 
-static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr, StepParams* sp = nullptr) {
+// `next` (optional): the batch of the FOLLOWING step, prepared by extra CTAs of this step's update kernel (step_fuse bit 2);
+// *next_done tells the caller whether that happened (only the fused tensor-core update kernel can do it).
+static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr, StepParams* sp = nullptr,
+                                    const PrepArgs* next = nullptr, size_t next_tile_bytes = 0, bool* next_done = nullptr) {
+    if (next_done) *next_done = false;
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
     const size_t np = net->n_params();
@@ -857,9 +913,15 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     if (B > 0) {
         const float* xb = net->xb.as<float>();
         const bool use_tc = net->precision != 0;
-        SZB_TRY(forward_rows(net, xb, B, true));
-        SZB_TRY(launch_softmax(net, B, 2, nullptr, net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), 0.f, nullptr,
-                               nullptr, use_tc ? net->zT.as<float>() : nullptr));
+        // layer 3 ends in softmax / cross-entropy: inside the GEMM's epilogue when a tile holds a whole row of logits, else
+        // as a kernel of its own
+        SoftmaxCe ce{net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), net->grads.as<float>() + np + 4 * net->tail_parity,
+                     net->zT.as<float>()};
+        bool ce_done = false;
+        SZB_TRY(forward_rows(net, xb, B, true, (use_tc && (ctx->step_fuse & 1)) ? &ce : nullptr, &ce_done));
+        if (!ce_done)
+            SZB_TRY(launch_softmax(net, B, 2, nullptr, net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), 0.f, nullptr,
+                                   nullptr, use_tc ? net->zT.as<float>() : nullptr));
         float* d3 = net->a_z.as<float>();
         const int C = int(net->n_out), H1 = int(net->h1), H2 = int(net->h2), I = int(net->n_in);
         if (use_tc) {
@@ -867,38 +929,55 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
                 const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
                 return std::max(1, ctx->sm_count / tiles);
             };
-            tc::GemmArgs g{};
+            tc::GemmArgs gw[3]{}, gx2{}, gx1{};
             // gW3[h2][C] = H2^T dZ                                                    (lib.rs:1029-1032)
-            g.A = net->h2T.as<float>(); g.lda = B; g.B = net->zT.as<float>(); g.ldb = B; g.C = G + net->off_w3(); g.ldc = C;
-            g.M = H2 + 1; g.N = C; g.K = B;      // row H2 of the product is sum_b dZ = the b3 gradient, which sits right
-            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H2 + 1, C)));   // behind w3 in the flattened gradient (lib.rs:1033)
-            // multi-GPU: [w3 | b3 | n_used, loss] is final -> reduce it across ranks while layers 2 and 1 run
-            if (!p2p) SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w3(), np + kGradTail - net->off_w3()));
+            gw[0].A = net->h2T.as<float>(); gw[0].lda = B; gw[0].B = net->zT.as<float>(); gw[0].ldb = B; gw[0].C = G + net->off_w3(); gw[0].ldc = C;
+            gw[0].M = H2 + 1; gw[0].N = C; gw[0].K = B;   // row H2 of the product is sum_b dZ = the b3 gradient, which sits right
+                                                          // behind w3 in the flattened gradient (lib.rs:1033)
             // d2 = (dZ W3^T) * (1 - H2^2)                                              (lib.rs:1034)
-            g = tc::GemmArgs{};
-            g.A = d3; g.lda = C; g.B = P + net->off_w3(); g.ldb = C; g.C = net->d_2.as<float>(); g.ldc = H2; g.CT = net->d2T.as<float>();
-            g.ldct = B; g.aux = net->h2T.as<float>(); g.ldaux = B; g.M = B; g.N = H2; g.K = C;   // factor read from H2^T: coalesced
-            SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, g));
+            gx2.A = d3; gx2.lda = C; gx2.B = P + net->off_w3(); gx2.ldb = C; gx2.C = net->d_2.as<float>(); gx2.ldc = H2; gx2.CT = net->d2T.as<float>();
+            gx2.ldct = B; gx2.aux = net->h2T.as<float>(); gx2.ldaux = B; gx2.M = B; gx2.N = H2; gx2.K = C;   // factor read from H2^T: coalesced
             // gW2[h1][h2] = H1^T d2                                                    (lib.rs:1035-1037)
-            g = tc::GemmArgs{};
-            g.A = net->h1T.as<float>(); g.lda = B; g.B = net->d2T.as<float>(); g.ldb = B; g.C = G + net->off_w2(); g.ldc = H2;
-            g.M = H1 + 1; g.N = H2; g.K = B;     // + b2 gradient (lib.rs:1038)
-            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(H1 + 1, H2)));
-            if (!p2p) SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w2(), net->off_w3() - net->off_w2()));
+            gw[1].A = net->h1T.as<float>(); gw[1].lda = B; gw[1].B = net->d2T.as<float>(); gw[1].ldb = B; gw[1].C = G + net->off_w2(); gw[1].ldc = H2;
+            gw[1].M = H1 + 1; gw[1].N = H2; gw[1].K = B;  // + b2 gradient (lib.rs:1038)
             // d1 = (d2 W2^T) * [H1 > 0]                                                (lib.rs:1039-1040)
-            g = tc::GemmArgs{};
             // only d1^T is consumed (by the layer-1 weight gradient): the row-major copy is not written
-            g.A = net->d_2.as<float>(); g.lda = H2; g.B = P + net->off_w2(); g.ldb = H2; g.C = nullptr; g.ldc = H1;
-            g.CT = net->d1T.as<float>(); g.ldct = B; g.aux = net->h1T.as<float>(); g.ldaux = B; g.M = B; g.N = H1; g.K = H2;
-            SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, g));
+            gx1.A = net->d_2.as<float>(); gx1.lda = H2; gx1.B = P + net->off_w2(); gx1.ldb = H2; gx1.C = nullptr; gx1.ldc = H1;
+            gx1.CT = net->d1T.as<float>(); gx1.ldct = B; gx1.aux = net->h1T.as<float>(); gx1.ldaux = B; gx1.M = B; gx1.N = H1; gx1.K = H2;
             // gW1[n_in][h1] = X^T d1                                                   (lib.rs:1041-1043)
-            g = tc::GemmArgs{};
-            g.A = net->xbT.as<float>(); g.lda = B; g.B = net->d1T.as<float>(); g.ldb = B; g.C = G + net->off_w1(); g.ldc = H1;
-            g.M = I + 1; g.N = H1; g.K = B;      // + b1 gradient (lib.rs:1044)
-            SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, g, split_for(I + 1, H1)));
-            if (!p2p) {
-                SZB_TRY(comm_allreduce_overlapped(ctx, G, net->off_w2()));
-                SZB_TRY(comm_join(ctx));
+            gw[2].A = net->xbT.as<float>(); gw[2].lda = B; gw[2].B = net->d1T.as<float>(); gw[2].ldb = B; gw[2].C = G + net->off_w1(); gw[2].ldc = H1;
+            gw[2].M = I + 1; gw[2].N = H1; gw[2].K = B;   // + b1 gradient (lib.rs:1044)
+            bool grouped = false;
+            if ((ctx->step_fuse & 4) && (p2p || ctx->world == 1)) {
+                // The weight gradients depend only on activations and deltas: the two input-gradient GEMMs (the dependent chain)
+                // go first, then all three weight gradients share ONE launch.  (With NCCL the per-layer order below is kept: each
+                // layer's all-reduce overlaps the GEMMs of the layers before it.)
+                SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, gx2));
+                SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, gx1));
+                if (net->precision == 2) SZB_TRY(tc::launch_gemm_tma_group<1>(ctx, gw, 3, &grouped));
+                else SZB_TRY(tc::launch_gemm_tma_group<3>(ctx, gw, 3, &grouped));
+                if (!grouped) {
+                    if (net->precision == 2) SZB_TRY(tc::launch_gemm_tc_group<1>(ctx, gw, 3, &grouped));
+                    else SZB_TRY(tc::launch_gemm_tc_group<3>(ctx, gw, 3, &grouped));
+                }
+                if (!grouped) {
+                    SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[0], split_for(H2 + 1, C)));
+                    SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[1], split_for(H1 + 1, H2)));
+                    SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[2], split_for(I + 1, H1)));
+                }
+            } else {
+                SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[0], split_for(H2 + 1, C)));
+                // multi-GPU: [w3 | b3 | n_used, loss] is final -> reduce it across ranks while layers 2 and 1 run
+                if (!p2p) SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w3(), np + kGradTail - net->off_w3()));
+                SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, gx2));
+                SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[1], split_for(H1 + 1, H2)));
+                if (!p2p) SZB_TRY(comm_allreduce_overlapped(ctx, G + net->off_w2(), net->off_w3() - net->off_w2()));
+                SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, gx1));
+                SZB_TRY(gemm_tc<tc::TC_ATOMIC>(net, gw[2], split_for(I + 1, H1)));
+                if (!p2p) {
+                    SZB_TRY(comm_allreduce_overlapped(ctx, G, net->off_w2()));
+                    SZB_TRY(comm_join(ctx));
+                }
             }
             reduced = true;
         } else {
@@ -962,7 +1041,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
         if (ctx->p2p_max_blocks == 0) {
             int per_sm_fused = 0, per_sm_plain = 0;
-            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 0));
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 48 * 1024));   // upper bound of a batch-preparing block's tile
             SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_plain, sgd_p2p_kernel, 256, 0));
             ctx->p2p_max_blocks = std::max(1, std::min(per_sm_fused, per_sm_plain)) * ctx->sm_count;
         }
@@ -973,10 +1052,16 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         const int tiles = int(((net->n_in + 31) / 32) * ((net->h1 + 31) / 32) + ((net->h1 + 31) / 32) * ((net->h2 + 31) / 32) +
                               ((net->h2 + 31) / 32) * ((net->n_out + 31) / 32));
         int blocks = std::max(1, std::min(tiles + 1, ctx->sm_count * 4));
-        if (p2p) blocks = std::min(blocks, p2p_blocks);
-        SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
-                            int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
-                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a, sp, B));
+        // extra CTAs gather, drop out and transpose the NEXT batch while these apply the update
+        const int next_blocks = (next && next->B > 0) ? (next->B + 31) / 32 : 0;
+        if (p2p) blocks = std::max(1, std::min(blocks, p2p_blocks - next_blocks));   // the exchanging CTAs wait for one another
+        a.nblk = blocks;
+        const PrepArgs none{};
+        SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks + next_blocks), dim3(256), next_blocks ? next_tile_bytes : size_t(0), P, G,
+                            net->wt.as<float>(), int(net->n_in), int(net->h1), int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(),
+                            net->off_b2(), net->off_w3(), net->off_b3(), net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr,
+                            net->stats.as<double>(), a, sp, B, next_blocks ? *next : none, blocks));
+        if (next_done) *next_done = next_blocks > 0;
     } else if (p2p) {
         const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(std::min(ctx->sm_count * 2, p2p_blocks))));
         sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, G, a, np, lr, net->stats.as<double>());
@@ -996,16 +1081,27 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     return SZB_OK;
 }
 
+static PrepArgs make_prep_args(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, int B,
+                               const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key, size_t* tile_bytes) {
+    PrepArgs a{};
+    a.feats = d_feats; a.labels_all = d_labels; a.perm = d_perm; a.B = B; a.n_in = int(net->n_in);
+    a.keep = d_keep; a.keep_by_row = keep_by_row; a.prob = prob; a.key = key;
+    a.xb = net->xb.as<float>(); a.xbT = net->precision != 0 ? net->xbT.as<float>() : nullptr;
+    a.lab = net->lab.as<uint32_t>(); a.valid = net->valid.as<uint8_t>();
+    a.h1T = net->h1T.as<float>(); a.h1 = int(net->h1); a.h2T = net->h2T.as<float>(); a.h2 = int(net->h2);
+    const size_t bytes = size_t(net->n_in) * 33 * sizeof(float);
+    a.use_tile = bytes <= 48 * 1024 ? 1 : 0;
+    *tile_bytes = a.use_tile ? bytes : size_t(0);
+    return a;
+}
+
 static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, int B,
                               const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key, const StepParams* sp = nullptr) {
     if (B <= 0) return SZB_OK;
     const int wpb = B >= 32 ? 32 : 8;     // one warp per row when the block's 32 rows exist: every gather load in flight at once
-    const size_t tile_bytes = size_t(net->n_in) * 33 * sizeof(float);
-    const int use_tile = tile_bytes <= 48 * 1024 ? 1 : 0;
-    SZB_CUDA(launch_pdl(net->ctx, prep_batch_kernel, dim3((B + 31) / 32), dim3(wpb * 32), use_tile ? tile_bytes : size_t(0), d_feats,
-                        d_labels, d_perm, B, int(net->n_in), d_keep, keep_by_row, prob, key, net->xb.as<float>(),
-                        net->precision != 0 ? net->xbT.as<float>() : nullptr, net->lab.as<uint32_t>(), net->valid.as<uint8_t>(),
-                        net->h1T.as<float>(), int(net->h1), net->h2T.as<float>(), int(net->h2), use_tile, sp));
+    size_t tile_bytes = 0;
+    const PrepArgs a = make_prep_args(net, d_feats, d_labels, d_perm, B, d_keep, keep_by_row, prob, key, &tile_bytes);
+    SZB_CUDA(launch_pdl(net->ctx, prep_batch_kernel, dim3((B + 31) / 32), dim3(wpb * 32), tile_bytes, a, sp));
     net->ctx->launches += 1;
     return SZB_OK;
 }
@@ -1028,6 +1124,7 @@ static szb_status capture_step_graph(szb_net* net, const StepGraphKey& k, float 
         if (st == SZB_OK) st = train_step_staged(net, k.B, nullptr, 0.f, sp);
     }
     const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
+    net->step_graph_kernels = uint32_t(ctx->launches - launches0);   // kernels in one replay (two steps)
     ctx->launches = launches0;                          // nothing ran
     if (st != SZB_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&net->step_graph, graph, 0) != cudaSuccess) {
         cudaGetLastError();
@@ -1293,10 +1390,23 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     }
     uint64_t s = 0;
     uint32_t i = 0;
+    // Large batches: the update kernel of step i also prepares the batch of step i + 1 (step_fuse bit 2), so only the first
+    // batch of an epoch costs a launch.  (Batches of <= 256 rows replay a captured graph whose steps prepare their own batch.)
+    const bool overlap_prep = (ctx->step_fuse & 2) && net->precision != 0 && step_sizes[0] > 256;
+    bool prepared = false;
     auto plain_step = [&]() -> szb_status {
         const int B = int(step_sizes[i]);
-        SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
-        SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
+        if (!prepared) SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
+        prepared = false;
+        const int B_next = (overlap_prep && i + 1 < n_steps) ? int(step_sizes[i + 1]) : 0;
+        if (B_next > 0) {
+            size_t tile_bytes = 0;
+            const PrepArgs next = make_prep_args(net, d_feats, d_labels, net->perm.as<uint32_t>() + s + step_sizes[i], B_next, d_keep, 1,
+                                                 dropout, key, &tile_bytes);
+            SZB_TRY(train_step_staged(net, B, nullptr, lr, nullptr, &next, tile_bytes, &prepared));
+        } else {
+            SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
+        }
         s += step_sizes[i];
         ++i;
         return SZB_OK;
@@ -1326,7 +1436,7 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
             SZB_CUDA(cudaMemcpyAsync(net->step_params.ptr, hp, sizeof(StepParams), cudaMemcpyHostToDevice, ctx->stream));
             SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
             for (uint32_t p = 0; p < n_pairs; ++p) SZB_CUDA(cudaGraphLaunch(net->step_graph, ctx->stream));
-            ctx->launches += uint64_t(n_pairs) * 22;     // 2 x (batch kernel, 8 GEMMs, softmax, update)
+            ctx->launches += uint64_t(n_pairs) * net->step_graph_kernels;   // 2 x (batch kernel, the step's GEMMs, [softmax,] update)
             ctx->graph_launches += n_pairs;
             i += 2 * n_pairs;
             s += uint64_t(2 * n_pairs) * uint64_t(B0);

@@ -48,6 +48,7 @@ struct szb_net {
     bool small_failed = false;
     szb::DevBuf step_params;
     cudaGraphExec_t step_graph = nullptr;
+    uint32_t step_graph_kernels = 0;   // kernel launches inside one replay of step_graph (two steps)
     szb::StepGraphKey step_graph_key;
     bool step_graph_failed = false;
     std::vector<std::vector<std::string>> file_lists;  // lib.rs:757, host-side only

@@ -391,3 +391,49 @@ def test_persistent_small_batch_kernel_equals_the_step_kernels_and_the_oracle(sz
         assert max(float(np.abs(a - b).max()) for a, b in zip(ws, wp)) <= 1e-4, dims
         assert np.abs(ps - oracle.forward(onet, feats[:4])).max() <= 1e-4        # the tensor-core forward sees the updated weights
     plain_ctx.close()
+
+
+def test_fused_step_launch_structure_equals_the_eleven_launch_step_and_the_oracle(sz, ctx, oracle, monkeypatch):
+    # Round 2's step was eleven launches (batch kernel, 3 forward GEMMs, softmax, dW3, dX2, dW2, dX1, dW1, update).  SZB_STEP_FUSE
+    # bits fold three of them away: 1 = softmax / cross-entropy in the layer-3 epilogue (n_out <= 128), 2 = the next batch
+    # prepared by extra CTAs of the update kernel (batches > 256 rows), 4 = input gradients first, then the three weight
+    # gradients as one grouped launch.  Every combination must give the eleven-launch result (to FP32 reassociation: the
+    # split-K ranges and the order of the softmax sum differ) and the oracle's, with ragged last batches (77 rows: rows of the
+    # transposed operands are no longer 16-byte aligned, the grouped launch falls back), windows dropped to all-zero, labels
+    # out of range, and more classes than one tile holds (200: softmax stays a kernel of its own).
+    r = np.random.default_rng(12)
+    for dims, batch, n in (((60, 512, 256, 100), 300, 300 * 3 + 77), ((60, 512, 256, 7), 260, 260 * 2 + 128), ((60, 512, 256, 200), 512, 1024 + 260)):
+        feats = r.standard_normal((n, dims[0])).astype(np.float32)
+        feats[5] = 0                                                            # a window that is all-zero before dropout
+        labels = r.integers(0, dims[3] + 1, n).astype(np.uint32)                # includes label == C: all-zero target (lib.rs:592-595)
+        base = oracle.Net.init(*dims, seed=6)
+        perms = [r.permutation(n).astype(np.uint32) for _ in range(2)]
+        outs = {}
+        for bits in (0, 1, 2, 4, 7):
+            monkeypatch.setenv("SZB_STEP_FUSE", str(bits))
+            c = sz.Context(0)
+            net = sz.SimpleNeuralNet.from_weights(*base.params(), ctx=c)
+            data = sz.DeviceFeatures(c, feats, labels)
+            l0 = c.launch_count
+            tot, cnt = 0.0, 0
+            for e, perm in enumerate(perms):
+                loss, used = sz.train_epoch(net, data, perm, batch, 0.02, dropout=0.2, seed=11, stream=e)
+                tot += loss; cnt += used
+            outs[bits] = (net.weights(), tot, cnt, c.launch_count - l0)
+            data.close(); net.close(); c.close()
+        monkeypatch.delenv("SZB_STEP_FUSE")
+        onet = base.copy()
+        otot, ocnt = 0.0, 0
+        for e, perm in enumerate(perms):
+            keep = oracle.dropout_keep_mask(11, e, np.arange(n), dims[0], 0.2)
+            l, k = oracle.train_epoch(onet, feats, labels, perm, batch, 0.02, keep)
+            otot += l; ocnt += k
+        w0, l0_, c0, n0 = outs[0]
+        for bits in (1, 2, 4, 7):
+            w, l, c, nl = outs[bits]
+            assert c == c0 == ocnt, (dims, bits, c, c0, ocnt)
+            assert abs(l - l0_) <= 1e-5 * abs(l0_) and abs(l - otot) <= 1e-3 * abs(otot), (dims, bits)
+            assert max(float(np.abs(a - b).max()) for a, b in zip(w, w0)) <= 2e-6, (dims, bits)
+            assert max(float(np.abs(a - b).max()) for a, b in zip(w, onet.params())) <= 1e-4, (dims, bits)
+            assert nl < n0 or (bits == 1 and dims[3] > 128), (dims, bits, nl, n0)      # launches really went away
+        assert outs[7][3] <= min(outs[b][3] for b in (1, 2, 4))

@@ -55,13 +55,22 @@ def _worker(rank, world, port, tmp):
             w4 = net2.weights()
         else:
             w3 = net2.weights()
+    # large batches (264 rows per rank): the update kernel of a step also prepares the next step's batch with extra CTAs that
+    # take no part in the exchange (SZB_STEP_FUSE bit 2); at world 4 / 8 the 1000 windows make a single, smaller step
+    ctx.comm_peer_exchange(True, "auto")
+    net5 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx)
+    for epoch in range(2):
+        local, sizes = shard_batches(d[f"perm{epoch}"], 264 * world, rank, world)
+        sz.train_epoch_steps(net5, data, local, sizes, 0.02, dropout=0.2, seed=77, stream=epoch)
+    w5 = net5.weights()
     ctx.comm_peer_exchange(False)
     # extraction: each rank takes its clip range, no collective
     clips = [d[f"clip{i}"] for i in range(6)]
     lo, hi = shard_clips([len(c) for c in clips], world)[rank]
     feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
     np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)},
-             **{f"r{i}": w for i, w in enumerate(w3)}, **{f"s{i}": w for i, w in enumerate(w4)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+             **{f"r{i}": w for i, w in enumerate(w3)}, **{f"s{i}": w for i, w in enumerate(w4)},
+             **{f"t{i}": w for i, w in enumerate(w5)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
     dist.destroy_process_group()
 
 
@@ -91,6 +100,9 @@ def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp
     net32 = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx).set_precision("fp32")
     for epoch in range(2):
         sz.train_epoch(net32, data, perms[epoch], 96, 0.02, dropout=0.2, seed=77, stream=epoch)
+    netb = sz.SimpleNeuralNet.from_weights(*onet.params(), ctx=ctx)
+    for epoch in range(2):
+        sz.train_epoch(netb, data, perms[epoch], 264 * world, 0.02, dropout=0.2, seed=77, stream=epoch)
     outs = [np.load(str(tmp_path / f"out{k}.npz")) for k in range(world)]
     for k in range(world):
         assert int(outs[k]["used"]) == cnt and abs(float(outs[k]["loss"]) - tot) <= 1e-3 * abs(tot)
@@ -98,6 +110,8 @@ def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp
             assert np.abs(outs[k][f"arr_{i}"] - w).max() <= 1e-5          # both replicas == the single-GPU result
             assert bool(outs[k]["peer"])                                  # B200 boxes have NVLink peer access
             assert np.abs(outs[k][f"q{i}"] - w).max() <= 1e-5             # ... with either gradient exchange
+        for i, w in enumerate(netb.weights()):
+            assert np.abs(outs[k][f"t{i}"] - w).max() <= 1e-5             # large batches: next batch prepared inside the update kernel
         for i, w in enumerate(net32.weights()):
             assert np.abs(outs[k][f"r{i}"] - w).max() <= 1e-5             # FP32 path: sgd_p2p_kernel
     for k in range(1, world):
@@ -105,6 +119,7 @@ def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp
             assert np.array_equal(outs[0][f"q{i}"], outs[k][f"q{i}"])     # broadcast (two-shot) or summed by every rank in the same
             assert np.array_equal(outs[0][f"r{i}"], outs[k][f"r{i}"])     # order (one-shot): bit-identical replicas
             assert np.array_equal(outs[0][f"s{i}"], outs[k][f"s{i}"])
+            assert np.array_equal(outs[0][f"t{i}"], outs[k][f"t{i}"])
     for i in range(6):
         assert np.array_equal(outs[0][f"q{i}"], outs[0][f"s{i}"])         # the two protocols add in the same order: same bits
     single = sz.FeatureExtractor(ctx).extract_batch(clips)

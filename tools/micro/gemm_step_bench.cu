@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace szb {
 void set_error(const char* fmt, ...) {
@@ -58,6 +59,14 @@ struct Job {
 
 template <int EPI>
 static szb_status run_epi(szb_ctx* ctx, const Job& j) {
+    if (ctx->gemm_tma) {                 // third generation: TMA operand fetch, two producer groups (gemm_tma.cuh)
+        bool done = false;
+        szb_status s;
+        if (j.passes == 1) s = j.narrow ? tc::launch_gemm_tma<64, 1, EPI>(ctx, j.g, j.split, &done) : tc::launch_gemm_tma<128, 1, EPI>(ctx, j.g, j.split, &done);
+        else s = j.narrow ? tc::launch_gemm_tma<64, 3, EPI>(ctx, j.g, j.split, &done) : tc::launch_gemm_tma<128, 3, EPI>(ctx, j.g, j.split, &done);
+        if (s != SZB_OK || done) return s;
+        fprintf(stderr, "TMA launch fell back\n");
+    }
     if (j.passes == 1)
         return j.narrow ? tc::launch_gemm_tc<64, 1, EPI>(ctx, j.g, j.split) : tc::launch_gemm_tc<128, 1, EPI>(ctx, j.g, j.split);
     return j.narrow ? tc::launch_gemm_tc<64, 3, EPI>(ctx, j.g, j.split) : tc::launch_gemm_tc<128, 3, EPI>(ctx, j.g, j.split);
@@ -81,7 +90,9 @@ int main(int argc, char** argv) {
     const int B = 4096, I = 60, H1 = 512, H2 = 256, C = 100;
     szb_ctx ctx;
     ctx.pdl = argc > 3 ? atoi(argv[3]) != 0 : true;
-    const bool use_ta = argc > 4 && atoi(argv[4]) != 0;      // A operand in tensor memory (gemm_tc_ta_kernel)
+    const int kernel_gen = argc > 4 ? atoi(argv[4]) : 0;     // 0: operands from shared memory, 1: A in tensor memory (gemm_tc_ta_kernel), 2: + TMA (gemm_tma_kernel)
+    const bool use_ta = kernel_gen != 0;
+    ctx.gemm_tma = false;
     CK(cudaSetDevice(0));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -153,6 +164,7 @@ int main(int argc, char** argv) {
             std::vector<float> c0(nc), c1(nc), t0(nt), t1(nt);
             for (int pass = 0; pass < 2; ++pass) {
                 ctx.gemm_ta = pass == 1;
+                ctx.gemm_tma = pass == 1 && kernel_gen == 2;
                 if (nc) CK(cudaMemsetAsync(j.g.C, 0, nc * 4, ctx.stream));
                 if (nt) CK(cudaMemsetAsync(j.g.CT, 0, nt * 4, ctx.stream));
                 run(&ctx, j);
@@ -167,8 +179,9 @@ int main(int argc, char** argv) {
             all_ok = all_ok && ok;
             printf("check %-20s C: max|diff| %.3e of max %.3e   CT: max|diff| %.3e of max %.3e   %s\n", j.name, dc, mc, dt, mt, ok ? "ok" : "MISMATCH");
         }
-        printf("A-in-TMEM kernel vs shared-memory kernel: %s\n", all_ok ? "all GEMMs agree" : "MISMATCH");
+        printf("generation-%d kernel vs shared-memory kernel: %s\n", kernel_gen, all_ok ? "all GEMMs agree" : "MISMATCH");
         ctx.gemm_ta = true;
+        ctx.gemm_tma = kernel_gen == 2;
     }
     std::vector<cudaEvent_t> ev(nj + 1);
     for (auto& e : ev) CK(cudaEventCreate(&e));
