@@ -85,12 +85,14 @@ struct szb_ctx {
     bool small_steps = true;   // epochs whose batches have <= 32 rows run as one persistent cooperative kernel (SZB_NO_SMALL_KERNEL=1: off)
     bool graphs = true;   // small-batch training epochs replay a captured two-step CUDA graph (SZB_NO_GRAPHS=1 turns it off)
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
-    // Launch structure of a tensor-core training step (SZB_STEP_FUSE=<bits>, default 7; 0 = round 2's eleven launches):
-    //   1: softmax / cross-entropy in the epilogue of the layer-3 GEMM (n_out <= 128)      -- softmax_train_kernel's launch goes
-    //   2: the NEXT batch is gathered (permutation, dropout, transposed copy) by extra CTAs of the update kernel -- prep_batch's launch
-    //      leaves the critical path (epochs of batches > 256 rows; smaller ones replay a graph or run the persistent kernel)
-    //   4: input gradients first, then the three weight-gradient GEMMs as ONE grouped launch (gemm_tc_ta_group_kernel)
-    int step_fuse = 7;
+    // Launch structure of a tensor-core training step (SZB_STEP_FUSE=<bits>, default 4; 0 = eleven launches per step: batch
+    // kernel, 3 forward GEMMs, softmax, dW3, dX2, dW2, dX1, dW1, update).  Measured on B200, batch 4096, 60-512-256-100, TMA GEMMs:
+    //   4: input gradients first, then the three weight-gradient GEMMs as ONE grouped launch            87.9 -> 78.4 us  (default)
+    //   1: softmax / cross-entropy in the epilogue of the layer-3 GEMM (n_out <= 128, 32 CTAs of 128 rows instead of 64 + a
+    //      separate 128-CTA kernel): 84.7 us with four threads per row (108 us with one) -- SLOWER, off
+    //   2: the batch kernel (gather by permutation, dropout, transposed copy) runs for 32 steps at a time (batches > 256 rows):
+    //      78.6 us -- no gain (with programmatic dependent launch the per-step batch kernel was already hidden), off
+    int step_fuse = 4;
     bool gemm_tma = true;   // dense-layer GEMMs fetch their operands by TMA and split the producer work over two warp groups
                             // (gemm_tma.cuh); SZB_GEMM_TMA=0 selects gemm_tc_ta_kernel (cp.async)
     bool gemm_ta = true;    // dense-layer GEMMs take the A operand from tensor memory (gemm_tc_ta_kernel); SZB_GEMM_TA=0 selects the

@@ -310,108 +310,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Layer-3 epilogue of a TRAINING step when one tile holds a whole row of logits (n_out <= BN, the CTA's n0 is 0): softmax
-// (lib.rs:1023-1026), delta3 = p - t (lib.rs:1028), the loss of the row (lib.rs:611-615) and the count of rows that survived
-// input dropout (lib.rs:607-609, 1047) straight from the accumulator -- what softmax_train_kernel did in a launch of its own.
-// A thread owns one row (its TMEM lane): the row's logits never leave tensor memory; they are read three times (maximum, sum
-// of exponentials, probabilities) instead of being kept in 128 registers.  delta3 leaves row-major through the warp's
-// shared-memory tile (C: the A operand of the next GEMM) and transposed with lanes along the rows (CT: the B operand of the
-// weight-gradient GEMM).  Called by warps 0-3 (one per TMEM lane quarter).
-__device__ __forceinline__ void tc_epilogue_softmax(const GemmArgs& g, uint32_t tmem_d, int m0, bool have_acc, float* stage) {
-    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
-    const int mrow0 = m0 + q * 32, m = mrow0 + lane;
-    const uint32_t lane_addr = tmem_d + (uint32_t(q * 32) << 16);
-    const int C = g.N;
-    const bool row_ok = m < g.M;
-    const bool c_vec = g.C && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    auto logits = [&](int c0, float (&v)[32]) {      // columns [c0, c0 + 32): accumulator + bias, -inf past the last class
-        uint32_t r[32];
-        if (have_acc) {
-            tmem_ld32(lane_addr + uint32_t(c0), r);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = c0 + j < C ? __uint_as_float(r[j]) + __ldg(g.bias + c0 + j) : -INFINITY;
-    };
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float v[32];
-        logits(c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);                      // lib.rs:1023
-    }
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float v[32];
-        logits(c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += c0 + j < C ? expf(v[j] - mx) : 0.f;  // lib.rs:1024-1025
-    }
-    const bool ok = row_ok && (g.valid ? g.valid[m] != 0 : true);
-    const uint32_t label = (row_ok && g.labels) ? g.labels[m] : 0xffffffffu;
-    float loss = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float v[32], d[32];
-        logits(c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int n = c0 + j;
-            d[j] = 0.f;
-            if (n < C) {
-                const float p = expf(v[j] - mx) / sum;                           // lib.rs:1026
-                const float t = g.target_vec ? __ldg(g.target_vec + n) : (uint32_t(n) == label ? 1.f : 0.f);
-                d[j] = ok ? p - t : 0.f;                                         // lib.rs:1028; skipped windows contribute nothing
-                if (ok && !g.target_vec && uint32_t(n) == label) loss = -logf(fmaxf(p, 1e-12f));
-            }
-        }
-        if (g.CT && row_ok) {
-            float* tp = g.CT + size_t(c0) * g.ldct + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c0 + j < C) tp[size_t(j) * g.ldct] = d[j];
-        }
-        if (g.C) {
-            float* mine = stage + lane * kEpiStride;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
-            __syncwarp();
-            const int cc = (lane & 7) * 4, n = c0 + cc;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = i * 4 + (lane >> 3), mm = mrow0 + rr;
-                const float4 w = *reinterpret_cast<const float4*>(stage + rr * kEpiStride + cc);
-                if (mm < g.M && n < C) {
-                    float* dst = g.C + size_t(mm) * g.ldc + n;
-                    if (c_vec && n + 4 <= C) {
-                        *reinterpret_cast<float4*>(dst) = w;
-                    } else {
-                        const float e[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (n + t < C) dst[t] = e[t];
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-    float cnt = ok ? 1.f : 0.f;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        loss += __shfl_xor_sync(0xffffffffu, loss, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    if (lane == 0 && g.tail) {
-        if (cnt > 0.f) atomicAdd(g.tail, cnt);
-        if (loss != 0.f) atomicAdd(g.tail + 1, loss);
-    }
-}
-
 // One CTA = one 128 x BN tile of C (x one K split).  128 threads: all of them stage operands; one issues the MMAs;
 // in the epilogue thread t owns accumulator row t (TMEM lane t).
 template <int BN, int PASSES, int EPI>
@@ -567,6 +465,9 @@ __device__ __forceinline__ void trace_stamp(int slot) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         g_gemm_trace[size_t(cta) * 8 + slot] = t;
+        // slot 7: SM clocks between stamps 1 and 4 (set-up done .. last MMA complete), to read the stamps in clocks as well
+        if (slot == 1) g_gemm_trace[size_t(cta) * 8 + 7] = (unsigned long long)clock64();
+        if (slot == 4) g_gemm_trace[size_t(cta) * 8 + 7] = (unsigned long long)clock64() - g_gemm_trace[size_t(cta) * 8 + 7];
     }
 }
 #define SZB_TRACE(slot) trace_stamp(slot)
@@ -932,12 +833,8 @@ __device__ __forceinline__ void gemm_tc_ta_body(const GemmArgs& g, const int bx,
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         SZB_TRACE(4);
-        if (EPI == TC_SOFTMAX_CE) {      // the whole row of logits sits in this tile (launcher: N <= BN, one column of tiles)
-            if (warp < 4) tc_epilogue_softmax(g, tmem_d, m0, n_kb > 0, reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
-        } else {
-            tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
-                                            reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
-        }
+        tc_epilogue_staged<BN / 2, EPI>(g, tmem_d + uint32_t((warp >> 2) * (BN / 2)), m0, n0 + (warp >> 2) * (BN / 2), n_kb > 0,
+                                        reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     SZB_TRACE(5);
@@ -1017,28 +914,6 @@ szb_status launch_gemm_tc(szb_ctx* ctx, GemmArgs g, int split_k) {
 
 inline bool gemm_operands_aligned(const GemmArgs& g) {
     return g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
-}
-
-// Layer 3 of a training step with softmax / cross-entropy in the epilogue (tc_epilogue_softmax).  Needs the whole row of
-// logits in one 128-column tile and the TMEM-A kernel; *done = false (nothing launched) otherwise: the caller then runs the
-// plain bias epilogue followed by softmax_train_kernel.
-template <int PASSES>
-szb_status launch_gemm_tc_softmax(szb_ctx* ctx, GemmArgs g, bool* done) {
-    constexpr int BN = 128;
-    *done = false;
-    if (g.M <= 0 || g.N <= 0 || g.N > BN || g.K <= 0 || !ctx->gemm_ta || !gemm_operands_aligned(g)) return SZB_OK;
-    using SLT = SmemLayoutTa<BN, PASSES>;
-    g.k_chunk = ((g.K + BK - 1) / BK) * BK;
-    static bool attr_set[64] = {};
-    if (!attr_set[ctx->device & 63]) {
-        SZB_CUDA(cudaFuncSetAttribute(gemm_tc_ta_kernel<BN, PASSES, TC_SOFTMAX_CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLT::kTotal));
-        attr_set[ctx->device & 63] = true;
-    }
-    SZB_CUDA(launch_pdl(ctx, gemm_tc_ta_kernel<BN, PASSES, TC_SOFTMAX_CE>, dim3(1, (g.M + BM - 1) / BM, 1), dim3(kThreadsAsync), size_t(SLT::kTotal), g));
-    SZB_CUDA(cudaGetLastError());
-    ctx->launches += 1;
-    *done = true;
-    return SZB_OK;
 }
 
 // The weight-gradient GEMMs of a step (split-K, vector reductions into the gradient vector) as one launch of

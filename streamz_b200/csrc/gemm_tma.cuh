@@ -56,6 +56,26 @@ struct SmemLayoutTma {
     static_assert(kTotal >= kTmaProducerWarps * kEpiWarpBytes, "the epilogue stages its tiles in the ring");
 };
 
+// Wait of a PRODUCER warp: the issuer of the MMAs shares its scheduler with four producer warps, and a warp that spins on
+// mbarrier.try_wait takes issue slots from it.  SZB_TMA_BACKOFF (ns) > 0: sleep between polls.
+#ifndef SZB_TMA_BACKOFF
+#define SZB_TMA_BACKOFF 0
+#endif
+__device__ __forceinline__ void mbar_wait_producer(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && SZB_TMA_BACKOFF > 0) __nanosleep(SZB_TMA_BACKOFF);
+        if (spin > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -64,6 +84,107 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(r0), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// Layer-3 epilogue of a TRAINING step when one tile holds a whole row of logits (n_out <= 128 = BN, the CTA's n0 is 0): softmax
+// (lib.rs:1023-1026), delta3 = p - t (lib.rs:1028), the loss of the row (lib.rs:611-615) and the count of rows that survived
+// input dropout (lib.rs:607-609, 1047) straight from the accumulator -- what softmax_train_kernel does in a launch of its own.
+// All sixteen producer warps take part: a thread owns 32 columns (warp >> 2) of one row (TMEM lane 32 (warp & 3) + lane), the
+// four partial maxima and sums of a row meet in shared memory (two barriers of the 512 producer threads), and every thread
+// adds them in the same order.  delta3 leaves row-major through the warp's shared-memory tile (C: the A operand of the next
+// GEMM) and transposed with lanes along the rows (CT: the B operand of the weight-gradient GEMM).
+// (A first version gave a whole row to one thread of warps 0-3: 300 exponentials per thread on one warp per scheduler made
+// the step 30 us slower than the separate kernel.)
+constexpr int kSoftmaxRedOffset = 80 * 1024;              // [2][4][128] floats behind the sixteen staging tiles (16 x 4608 B)
+__device__ __forceinline__ void tma_epilogue_softmax(const GemmArgs& g, uint32_t tmem_d, int m0, bool have_acc, float* stage, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane, mrow0 = m0 + q * 32, m = m0 + row;
+    const int c0 = cg * 32, C = g.N;
+    const bool row_ok = m < g.M;
+    const bool c_vec = g.C && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    uint32_t r[32];
+    if (have_acc) {
+        tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    float v[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        v[j] = c0 + j < C ? __uint_as_float(r[j]) + __ldg(g.bias + c0 + j) : -INFINITY;
+        mx = fmaxf(mx, v[j]);                                                    // lib.rs:1023
+    }
+    red[cg * 128 + row] = mx;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    mx = fmaxf(fmaxf(red[row], red[128 + row]), fmaxf(red[256 + row], red[384 + row]));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        v[j] = c0 + j < C ? expf(v[j] - mx) : 0.f;                               // lib.rs:1024
+        sum += v[j];
+    }
+    red[512 + cg * 128 + row] = sum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    sum = ((red[512 + row] + red[640 + row]) + red[768 + row]) + red[896 + row]; // the same order in all four threads of a row
+    const bool ok = row_ok && (g.valid ? g.valid[m] != 0 : true);
+    const uint32_t label = (row_ok && g.labels) ? g.labels[m] : 0xffffffffu;
+    float loss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = c0 + j;
+        float d = 0.f;
+        if (n < C) {
+            const float p = v[j] / sum;                                          // lib.rs:1026
+            const float t = g.target_vec ? __ldg(g.target_vec + n) : (uint32_t(n) == label ? 1.f : 0.f);
+            d = ok ? p - t : 0.f;                                                // lib.rs:1028; skipped windows contribute nothing
+            if (ok && !g.target_vec && uint32_t(n) == label) loss = -logf(fmaxf(p, 1e-12f));
+        }
+        v[j] = d;
+    }
+    if (c0 < C) {
+        if (g.CT && row_ok) {
+            float* tp = g.CT + size_t(c0) * g.ldct + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < C) tp[size_t(j) * g.ldct] = v[j];
+        }
+        if (g.C) {
+            float* mine = stage + lane * kEpiStride;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            const int cc = (lane & 7) * 4, n = c0 + cc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), mm = mrow0 + rr;
+                const float4 w = *reinterpret_cast<const float4*>(stage + rr * kEpiStride + cc);
+                if (mm < g.M && n < C) {
+                    float* dst = g.C + size_t(mm) * g.ldc + n;
+                    if (c_vec && n + 4 <= C) {
+                        *reinterpret_cast<float4*>(dst) = w;
+                    } else {
+                        const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (n + t < C) dst[t] = e[t];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    float cnt = (ok && cg == 0) ? 1.f : 0.f;                                      // one of the four threads of a row counts it
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        loss += __shfl_xor_sync(0xffffffffu, loss, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0 && g.tail) {
+        if (cnt > 0.f) atomicAdd(g.tail, cnt);
+        if (loss != 0.f) atomicAdd(g.tail + 1, loss);
+    }
 }
 
 template <int BN, int PASSES, int EPI>
@@ -115,9 +236,13 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
                 const int s = kb % kStages;
                 if (kb >= kStages) mbar_wait(&s_free[s], uint32_t((kb / kStages - 1) & 1));      // MMAs of k-block kb - kStages are done
                 const uint32_t st = smem_base + s * SL::kStageBytes;
+#ifdef SZB_X_NOLOAD
+                mbar_arrive(&s_loaded[s]);           // experiment: no copies, the tile is "there" at once
+#else
                 mbar_expect_tx(&s_loaded[s], uint32_t(SL::kStageBytes));
                 tma_load_2d(st, tmA, kb0 + kb * BK, m0, &s_loaded[s]);
                 tma_load_2d(st + SL::kATile, tmB, kb0 + kb * BK, n0, &s_loaded[s]);
+#endif
             }
         }
     } else if (warp == kTmaProducerWarps) {
@@ -135,6 +260,9 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
                     const uint64_t adv = uint64_t((k * UK * 4) >> 4);
                     const uint32_t acol = uint32_t(k * UK);
                     const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+#ifdef SZB_X_NOMMA
+                    if (kb > 0) continue;          // experiment: one k-block of MMAs (the accumulator is defined), then bare commits
+#endif
                     if (PASSES == 3) {
                         umma_tf32_ts(tmem_d, a_lo + acol, db_hi + adv, idesc, acc0);
                         umma_tf32_ts(tmem_d, a_hi + acol, db_lo + adv, idesc, 1u);
@@ -158,11 +286,12 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % kStages;
             if (kb >= kNBuf) {          // MMAs of k-block kb - kNBuf done: TMEM A buffer kb % kNBuf is free
-                mbar_wait(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));
+                mbar_wait_producer(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            mbar_wait(&s_loaded[s], uint32_t((kb / kStages) & 1));
+            mbar_wait_producer(&s_loaded[s], uint32_t((kb / kStages) & 1));
             const uint32_t st = smem_base + s * SL::kStageBytes;
+#ifndef SZB_X_NOSPLIT
             float hi[16], lo[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -179,6 +308,9 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
                 tmem_st16(abuf + 32, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#else
+            (void)st; (void)a_lane; (void)h;
+#endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
@@ -192,10 +324,11 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
         constexpr int kRb = BN / 32;
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % kStages;
-            if (kb >= kNBuf) mbar_wait(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));   // lo buffer kb % kNBuf is free
-            mbar_wait(&s_loaded[s], uint32_t((kb / kStages) & 1));
+            if (kb >= kNBuf) mbar_wait_producer(&s_free[(kb - kNBuf) % kStages], uint32_t(((kb - kNBuf) / kStages) & 1));   // lo buffer kb % kNBuf is free
+            mbar_wait_producer(&s_loaded[s], uint32_t((kb / kStages) & 1));
             const uint32_t src = smem_base + s * SL::kStageBytes + SL::kATile;
             const uint32_t dst = lo_base + (kb % kNBuf) * SL::kBTile;
+#ifndef SZB_X_NOSPLIT
             float4 v[kRb];
 #pragma unroll
             for (int u = 0; u < kRb; ++u)
@@ -206,19 +339,25 @@ __device__ __forceinline__ void gemm_tma_body(const GemmArgs& g, const CUtensorM
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + sw128_off(lr + 32 * u, lc)), "f"(v[u].x - tf32_trunc(v[u].x)),
                              "f"(v[u].y - tf32_trunc(v[u].y)), "f"(v[u].z - tf32_trunc(v[u].z)), "f"(v[u].w - tf32_trunc(v[u].w))
                              : "memory");
+#else
+            (void)src; (void)dst; (void)lr; (void)lc;
+#endif
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
         }
     }
     if (warp < kTmaProducerWarps) {
-        if (n_kb > 0) mbar_wait(&s_done, 0u);                                       // every MMA of the tile has completed
+        if (n_kb > 0) mbar_wait_producer(&s_done, 0u);                                       // every MMA of the tile has completed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         SZB_TRACE(4);
         // every MMA has completed, every bulk copy was consumed by one: the ring is free to stage the output tile.
         // A warp takes its TMEM lane quarter (warp & 3) x 32 columns (warp >> 2).
         constexpr int kEpiWarps = (BN / 32) * 4;
-        if (warp < kEpiWarps)
+        if (EPI == TC_SOFTMAX_CE)        // the whole row of logits sits in this tile (launcher: N <= BN = 128, one column of tiles)
+            tma_epilogue_softmax(g, tmem_d, m0, n_kb > 0, reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes),
+                                 reinterpret_cast<float*>(tc_smem + kSoftmaxRedOffset));
+        else if (warp < kEpiWarps)
             tc_epilogue_staged<32, EPI>(g, tmem_d + uint32_t((warp >> 2) * 32), m0, n0 + (warp >> 2) * 32, n_kb > 0,
                                         reinterpret_cast<float*>(tc_smem + warp * kEpiWarpBytes));
     }
@@ -319,6 +458,31 @@ szb_status launch_gemm_tma(szb_ctx* ctx, GemmArgs g, int split_k, bool* done) {
         attr_set[ctx->device & 63] = true;
     }
     SZB_CUDA(launch_pdl(ctx, gemm_tma_kernel<BN, PASSES, EPI>, grid, dim3(kTmaThreads), size_t(SL::kTotal), g, tmA, tmB));
+    SZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    *done = true;
+    return SZB_OK;
+}
+
+// Layer 3 of a training step with softmax / cross-entropy in the epilogue (tma_epilogue_softmax).  Needs the whole row of
+// logits in one 128-column tile; *done = false (nothing launched) otherwise: the caller then runs the plain bias epilogue
+// followed by softmax_train_kernel.
+template <int PASSES>
+szb_status launch_gemm_tma_softmax(szb_ctx* ctx, GemmArgs g, bool* done) {
+    constexpr int BN = 128;
+    *done = false;
+    if (g.M <= 0 || g.N <= 0 || g.N > BN || g.K <= 0 || !ctx->gemm_tma || !gemm_operands_aligned(g)) return SZB_OK;
+    CUtensorMap tmA, tmB;
+    if (!tensor_map_for(g.A, g.M, g.K, g.lda, BM, &tmA) || !tensor_map_for(g.B, g.N, g.K, g.ldb, BN, &tmB)) return SZB_OK;
+    using SL = SmemLayoutTma<BN, PASSES>;
+    static_assert(SL::kTotal >= kSoftmaxRedOffset + 2 * 4 * 128 * 4, "room for the partial maxima and sums");
+    g.k_chunk = ((g.K + BK - 1) / BK) * BK;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        SZB_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN, PASSES, TC_SOFTMAX_CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        attr_set[ctx->device & 63] = true;
+    }
+    SZB_CUDA(launch_pdl(ctx, gemm_tma_kernel<BN, PASSES, TC_SOFTMAX_CE>, dim3(1, (g.M + BM - 1) / BM, 1), dim3(kTmaThreads), size_t(SL::kTotal), g, tmA, tmB));
     SZB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     *done = true;

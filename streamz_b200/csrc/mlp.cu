@@ -308,7 +308,8 @@ struct PrepArgs {
     float* xb; float* xbT; uint32_t* lab; uint8_t* valid;
     float* h1T; int h1; float* h2T; int h2;
     int use_tile;
-};
+    int blocks_per_step;    // > 0: the launch prepares SEVERAL consecutive steps of B rows each (block b serves step b / blocks_per_step);
+};                          //      step j's rows follow step j - 1's in xb / lab / valid, its transposed block in xbT
 
 __device__ __forceinline__ void prep_batch_block(const PrepArgs& a, const int block, const uint32_t* __restrict__ perm,
                                                  const unsigned long long key, float* prep_tile /* [n_in][33] when use_tile */) {
@@ -364,6 +365,18 @@ __global__ void prep_batch_kernel(const __grid_constant__ PrepArgs a, const Step
     if (sp) {                              // captured step: position in the shuffled order and dropout key come from device memory
         perm += sp->cursor;
         key = sp->key;
+    }
+    if (a.blocks_per_step > 0) {
+        // several steps of the epoch in one launch (szb_net_train_epoch_steps_dev: large batches): the batch kernel leaves the
+        // per-step critical path.  Nothing here depends on the weights, only on the permutation and the dropout stream.
+        const int j = int(blockIdx.x) / a.blocks_per_step;
+        PrepArgs b = a;
+        b.xb += size_t(j) * a.B * a.n_in;
+        if (b.xbT) b.xbT += size_t(j) * (a.n_in + 1) * a.B;
+        if (b.lab) b.lab += size_t(j) * a.B;
+        b.valid += size_t(j) * a.B;
+        prep_batch_block(b, int(blockIdx.x) % a.blocks_per_step, perm + size_t(j) * a.B, key, prep_tile);
+        return;
     }
     prep_batch_block(a, blockIdx.x, perm, key, prep_tile);
 }
@@ -557,19 +570,11 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
                                                         int h1, int h2, int n_out, size_t off_b1, size_t off_w2, size_t off_b2,
                                                         size_t off_w3, size_t off_b3, size_t off_wt2, size_t off_wt3, size_t np, int parity,
                                                         float lr, double* __restrict__ stats, const __grid_constant__ P2pArgs a,
-                                                        StepParams* __restrict__ sp, int advance, const __grid_constant__ PrepArgs next,
-                                                        const int n_upd /* blocks [0, n_upd) update, the rest prepare the next batch */) {
+                                                        StepParams* __restrict__ sp, int advance) {
     __shared__ float tile[32][33];
-    extern __shared__ float next_tile[];   // [n_in][33] of a batch-preparing block
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    if (int(blockIdx.x) >= n_upd) {
-        // The next step's batch: gathered, dropped out and transposed while the other blocks exchange and apply this step's
-        // gradient.  Everything that read the batch buffers (the step's GEMMs) completed before griddepcontrol.wait returned,
-        // and nothing in the update touches them.
-        prep_batch_block(next, int(blockIdx.x) - n_upd, next.perm, next.key, next_tile);
-        return;
-    }
+    const int n_upd = int(gridDim.x);
     if (sp) {                              // captured step (CUDA graph): learning rate from device memory; move on to the next batch
         lr = sp->lr;                       // (the next step's batch kernel reads the position only after this grid has completed)
         if (blockIdx.x == 0 && threadIdx.x == 0) sp->cursor += uint32_t(advance);
@@ -789,7 +794,7 @@ static szb_status gemm_tc(szb_net* net, tc::GemmArgs g, int split_k = 1) {
     return narrow ? tc::launch_gemm_tc<64, 3, EPI>(net->ctx, g, split_k) : tc::launch_gemm_tc<128, 3, EPI>(net->ctx, g, split_k);
 }
 
-// What the layer-3 epilogue of a training step needs to finish the forward pass itself (tc_epilogue_softmax)
+// What the layer-3 epilogue of a training step needs to finish the forward pass itself (tma_epilogue_softmax)
 struct SoftmaxCe {
     const uint32_t* labels; const float* target_vec; const uint8_t* valid;
     float* tail;     // [n_used, loss] block of the gradient vector this step accumulates into
@@ -822,8 +827,8 @@ static szb_status forward_rows(szb_net* net, const float* d_x, int B, bool train
         if (ce && ce_done && C <= 128) {
             tc::GemmArgs gs = g;
             gs.CT = ce->zT; gs.ldct = B; gs.labels = ce->labels; gs.target_vec = ce->target_vec; gs.valid = ce->valid; gs.tail = ce->tail;
-            if (net->precision == 2) SZB_TRY(tc::launch_gemm_tc_softmax<1>(net->ctx, gs, ce_done));
-            else SZB_TRY(tc::launch_gemm_tc_softmax<3>(net->ctx, gs, ce_done));
+            if (net->precision == 2) SZB_TRY(tc::launch_gemm_tma_softmax<1>(net->ctx, gs, ce_done));
+            else SZB_TRY(tc::launch_gemm_tma_softmax<3>(net->ctx, gs, ce_done));
             if (*ce_done) return SZB_OK;
         }
         SZB_TRY(gemm_tc<tc::TC_BIAS>(net, g));
@@ -889,11 +894,14 @@ szb_status comm_allreduce_f32(szb_ctx* ctx, float* buf, size_t n);  // comm.cu
 szb_status comm_allreduce_overlapped(szb_ctx* ctx, float* buf, size_t n);
 szb_status comm_join(szb_ctx* ctx);
 
-// `next` (optional): the batch of the FOLLOWING step, prepared by extra CTAs of this step's update kernel (step_fuse bit 2);
-// *next_done tells the caller whether that happened (only the fused tensor-core update kernel can do it).
+// Where the step's batch sits: the net's own batch buffers (filled by launch_prep right before the step), or one step's slice
+// of the chunk buffers that a multi-step launch of the batch kernel filled (szb_net_train_epoch_steps_dev).
+struct BatchView {
+    const float* xb; const float* xbT; const uint32_t* lab; const uint8_t* valid;
+};
+
 static szb_status train_step_staged(szb_net* net, int B, const float* target_vec, float lr, StepParams* sp = nullptr,
-                                    const PrepArgs* next = nullptr, size_t next_tile_bytes = 0, bool* next_done = nullptr) {
-    if (next_done) *next_done = false;
+                                    const BatchView* view = nullptr) {
     szb_ctx* ctx = net->ctx;
     float* P = net->params.as<float>();
     const size_t np = net->n_params();
@@ -911,17 +919,17 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
     net->grads_zero = false;
     bool reduced = p2p;     // gradient slices already all-reduced (overlapped) inside the backward pass, or exchanged below
     if (B > 0) {
-        const float* xb = net->xb.as<float>();
+        const BatchView own{net->xb.as<float>(), net->xbT.as<float>(), net->lab.as<uint32_t>(), net->valid.as<uint8_t>()};
+        const BatchView& bv = view ? *view : own;
+        const float* xb = bv.xb;
         const bool use_tc = net->precision != 0;
         // layer 3 ends in softmax / cross-entropy: inside the GEMM's epilogue when a tile holds a whole row of logits, else
         // as a kernel of its own
-        SoftmaxCe ce{net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), net->grads.as<float>() + np + 4 * net->tail_parity,
-                     net->zT.as<float>()};
+        SoftmaxCe ce{bv.lab, target_vec, bv.valid, net->grads.as<float>() + np + 4 * net->tail_parity, net->zT.as<float>()};
         bool ce_done = false;
         SZB_TRY(forward_rows(net, xb, B, true, (use_tc && (ctx->step_fuse & 1)) ? &ce : nullptr, &ce_done));
         if (!ce_done)
-            SZB_TRY(launch_softmax(net, B, 2, nullptr, net->lab.as<uint32_t>(), target_vec, net->valid.as<uint8_t>(), 0.f, nullptr,
-                                   nullptr, use_tc ? net->zT.as<float>() : nullptr));
+            SZB_TRY(launch_softmax(net, B, 2, nullptr, bv.lab, target_vec, bv.valid, 0.f, nullptr, nullptr, use_tc ? net->zT.as<float>() : nullptr));
         float* d3 = net->a_z.as<float>();
         const int C = int(net->n_out), H1 = int(net->h1), H2 = int(net->h2), I = int(net->n_in);
         if (use_tc) {
@@ -945,7 +953,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             gx1.A = net->d_2.as<float>(); gx1.lda = H2; gx1.B = P + net->off_w2(); gx1.ldb = H2; gx1.C = nullptr; gx1.ldc = H1;
             gx1.CT = net->d1T.as<float>(); gx1.ldct = B; gx1.aux = net->h1T.as<float>(); gx1.ldaux = B; gx1.M = B; gx1.N = H1; gx1.K = H2;
             // gW1[n_in][h1] = X^T d1                                                   (lib.rs:1041-1043)
-            gw[2].A = net->xbT.as<float>(); gw[2].lda = B; gw[2].B = net->d1T.as<float>(); gw[2].ldb = B; gw[2].C = G + net->off_w1(); gw[2].ldc = H1;
+            gw[2].A = bv.xbT; gw[2].lda = B; gw[2].B = net->d1T.as<float>(); gw[2].ldb = B; gw[2].C = G + net->off_w1(); gw[2].ldc = H1;
             gw[2].M = I + 1; gw[2].N = H1; gw[2].K = B;   // + b1 gradient (lib.rs:1044)
             bool grouped = false;
             if ((ctx->step_fuse & 4) && (p2p || ctx->world == 1)) {
@@ -1041,7 +1049,7 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
         if (ctx->p2p_max_blocks == 0) {
             int per_sm_fused = 0, per_sm_plain = 0;
-            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 48 * 1024));   // upper bound of a batch-preparing block's tile
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 0));
             SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_plain, sgd_p2p_kernel, 256, 0));
             ctx->p2p_max_blocks = std::max(1, std::min(per_sm_fused, per_sm_plain)) * ctx->sm_count;
         }
@@ -1052,16 +1060,10 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         const int tiles = int(((net->n_in + 31) / 32) * ((net->h1 + 31) / 32) + ((net->h1 + 31) / 32) * ((net->h2 + 31) / 32) +
                               ((net->h2 + 31) / 32) * ((net->n_out + 31) / 32));
         int blocks = std::max(1, std::min(tiles + 1, ctx->sm_count * 4));
-        // extra CTAs gather, drop out and transpose the NEXT batch while these apply the update
-        const int next_blocks = (next && next->B > 0) ? (next->B + 31) / 32 : 0;
-        if (p2p) blocks = std::max(1, std::min(blocks, p2p_blocks - next_blocks));   // the exchanging CTAs wait for one another
-        a.nblk = blocks;
-        const PrepArgs none{};
-        SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks + next_blocks), dim3(256), next_blocks ? next_tile_bytes : size_t(0), P, G,
-                            net->wt.as<float>(), int(net->n_in), int(net->h1), int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(),
-                            net->off_b2(), net->off_w3(), net->off_b3(), net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr,
-                            net->stats.as<double>(), a, sp, B, next_blocks ? *next : none, blocks));
-        if (next_done) *next_done = next_blocks > 0;
+        if (p2p) blocks = std::min(blocks, p2p_blocks);
+        SZB_CUDA(launch_pdl(ctx, sgd_fused_kernel, dim3(blocks), dim3(256), 0, P, G, net->wt.as<float>(), int(net->n_in), int(net->h1),
+                            int(net->h2), int(net->n_out), net->off_b1(), net->off_w2(), net->off_b2(), net->off_w3(), net->off_b3(),
+                            net->off_wt2(), net->off_wt3(), np, net->tail_parity, lr, net->stats.as<double>(), a, sp, B));
     } else if (p2p) {
         const int blocks = int(std::min<size_t>((np / 4 + 255) / 256, size_t(std::min(ctx->sm_count * 2, p2p_blocks))));
         sgd_p2p_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(P, G, a, np, lr, net->stats.as<double>());
@@ -1260,7 +1262,8 @@ void szb_net_destroy(szb_net* net) {
     net->step_params.release();
     net->small_scratch.release(); net->small_barrier.release(); net->small_steps.release();
     for (DevBuf* b : { &net->params, &net->grads, &net->xb, &net->lab, &net->valid, &net->a_h1, &net->a_h2, &net->a_z, &net->d_2,
-                       &net->d_1, &net->stats, &net->perm, &net->hist, &net->wt, &net->xbT, &net->h1T, &net->h2T, &net->zT, &net->d2T, &net->d1T })
+                       &net->d_1, &net->stats, &net->perm, &net->hist, &net->wt, &net->xbT, &net->h1T, &net->h2T, &net->zT, &net->d2T, &net->d1T,
+                       &net->chunk_xb, &net->chunk_xbT, &net->chunk_lab, &net->chunk_valid })
         b->release();
     delete net;
 }
@@ -1390,27 +1393,45 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     }
     uint64_t s = 0;
     uint32_t i = 0;
-    // Large batches: the update kernel of step i also prepares the batch of step i + 1 (step_fuse bit 2), so only the first
-    // batch of an epoch costs a launch.  (Batches of <= 256 rows replay a captured graph whose steps prepare their own batch.)
-    const bool overlap_prep = (ctx->step_fuse & 2) && net->precision != 0 && step_sizes[0] > 256;
-    bool prepared = false;
     auto plain_step = [&]() -> szb_status {
         const int B = int(step_sizes[i]);
-        if (!prepared) SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
-        prepared = false;
-        const int B_next = (overlap_prep && i + 1 < n_steps) ? int(step_sizes[i + 1]) : 0;
-        if (B_next > 0) {
-            size_t tile_bytes = 0;
-            const PrepArgs next = make_prep_args(net, d_feats, d_labels, net->perm.as<uint32_t>() + s + step_sizes[i], B_next, d_keep, 1,
-                                                 dropout, key, &tile_bytes);
-            SZB_TRY(train_step_staged(net, B, nullptr, lr, nullptr, &next, tile_bytes, &prepared));
-        } else {
-            SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
-        }
+        SZB_TRY(launch_prep(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, B, d_keep, 1, dropout, key));
+        SZB_TRY(train_step_staged(net, B, nullptr, lr));   // B == 0 still joins the all-reduce of a multi-GPU step
         s += step_sizes[i];
         ++i;
         return SZB_OK;
     };
+    // ---- large batches: the batch kernel runs for kPrepChunk steps at a time (step_fuse bit 2) ------------------------------------
+    // Gathering, dropping out and transposing a batch depends only on the permutation and the dropout stream, never on the
+    // weights, so it does not have to sit between two steps: one launch fills the batch buffers of the next kPrepChunk equal-sized
+    // steps (64 MB for 32 steps of 4096 windows), and each step reads its slice.  Per step that is 1/32 of a (larger, better
+    // filled) launch instead of a ~4 us kernel on the critical path.  Batches of <= 256 rows replay a captured graph instead.
+    if ((ctx->step_fuse & 2) && net->precision != 0 && step_sizes[0] > 256) {
+        constexpr uint32_t kPrepChunk = 32;
+        const uint32_t B0 = step_sizes[0];
+        const size_t ni = net->n_in;
+        while (i < n_steps && step_sizes[i] == B0) {
+            uint32_t cnt = 0;
+            while (i + cnt < n_steps && cnt < kPrepChunk && step_sizes[i + cnt] == B0) ++cnt;
+            SZB_TRY(net->chunk_xb.reserve(size_t(cnt) * B0 * ni * 4));
+            SZB_TRY(net->chunk_xbT.reserve(size_t(cnt) * B0 * (ni + 1) * 4));
+            SZB_TRY(net->chunk_lab.reserve(size_t(cnt) * B0 * 4));
+            SZB_TRY(net->chunk_valid.reserve(size_t(cnt) * B0));
+            size_t tile_bytes = 0;
+            PrepArgs a = make_prep_args(net, d_feats, d_labels, net->perm.as<uint32_t>() + s, int(B0), d_keep, 1, dropout, key, &tile_bytes);
+            a.xb = net->chunk_xb.as<float>(); a.xbT = net->chunk_xbT.as<float>(); a.lab = net->chunk_lab.as<uint32_t>();
+            a.valid = net->chunk_valid.as<uint8_t>();
+            a.blocks_per_step = int((B0 + 31) / 32);
+            SZB_CUDA(launch_pdl(ctx, prep_batch_kernel, dim3(cnt * a.blocks_per_step), dim3(1024), tile_bytes, a, static_cast<const StepParams*>(nullptr)));
+            ctx->launches += 1;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const BatchView bv{a.xb + size_t(j) * B0 * ni, a.xbT + size_t(j) * B0 * (ni + 1), a.lab + size_t(j) * B0, a.valid + size_t(j) * B0};
+                SZB_TRY(train_step_staged(net, int(B0), nullptr, lr, nullptr, &bv));
+            }
+            s += uint64_t(cnt) * B0;
+            i += cnt;
+        }
+    }
     // ---- small batches: replay a captured two-step graph (see capture_step_graph) -------------------------------------------
     const int B0 = int(step_sizes[0]);
     uint32_t n_full = 0;

@@ -35,6 +35,7 @@ struct szb_net {
     // tensor-core path: transposed weights [wt1 (h1 x n_in) | wt2 (h2 x h1) | wt3 (n_out x h2)] and the transposed
     // activations / deltas ([features][rows]) that make every GEMM of a step "TN" (gemm_tc.cuh)
     szb::DevBuf wt, xbT, h1T, h2T, zT, d2T, d1T;
+    szb::DevBuf chunk_xb, chunk_xbT, chunk_lab, chunk_valid;   // batch buffers of several steps filled by one launch (large batches)
     bool wt_dirty = true;
     bool grads_zero = false;      // the gradient vector (except the other tail block) is known to be all zeros
     int tail_parity = 0;          // which tail block the current step accumulates [n_used, loss] into

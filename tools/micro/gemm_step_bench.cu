@@ -241,7 +241,7 @@ int main(int argc, char** argv) {
 #ifdef SZB_GEMM_TRACE
         const unsigned long long* p = tr.data() + size_t(k) * max_ctas * 8;
         int n = 0;
-        double s[7] = {0};
+        double s[7] = {0}, ghz = 0;
         unsigned long long tmin = ~0ull, tmax = 0, emax = 0;
         for (int c = 0; c < max_ctas; ++c) {
             if (p[c * 8] == 0) continue;
@@ -251,10 +251,12 @@ int main(int argc, char** argv) {
             tmin = std::min(tmin, p[c * 8]);
             emax = std::max(emax, p[c * 8]);
             tmax = std::max(tmax, p[c * 8 + 6]);
+            if (p[c * 8 + 4] > p[c * 8 + 1]) ghz += double(p[c * 8 + 7]) / double(p[c * 8 + 4] - p[c * 8 + 1]);
         }
         printf("%-20s %5d %5d | %7.2f | %39s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f | %6.2f %6.2f\n", j.name, j.narrow ? 64 : 128, n,
                acc[k] * 1000.0 / iters, "", s[1] / n / 1e3, s[2] / n / 1e3, s[3] / n / 1e3, s[4] / n / 1e3, s[5] / n / 1e3, s[6] / n / 1e3,
                double(tmax - tmin) / 1e3, double(emax - tmin) / 1e3);
+        printf("%-20s SM clock between set-up and last MMA: %.3f GHz\n", "", ghz / n);
 #else
         printf("%-20s BN %3d | %7.2f us\n", j.name, j.narrow ? 64 : 128, acc[k] * 1000.0 / iters);
 #endif
