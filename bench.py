@@ -336,13 +336,15 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
            "windows": nwin, "speakers": MLP_SPEAKERS, "batch_per_gpu": MLP_BATCH, "mean_loss": runs[best]["mean_loss"],
            "tflops": world * tflops, "gpu_launches": runs[best]["launches"],
            "precision": "3xTF32 (tcgen05 kind::tf32, split hi/lo, FP32-equivalent); tflops counts algorithmic FLOPs once",
+           "kernels": "gemm_tma_kernel: TMA operand fetch, A operand and accumulator in tensor memory; weight gradients as one grouped launch",
            "grad_exchange": best, "exchange_timings": runs, "replicas_identical": all(r["replicas_identical"] for r in runs.values()),
            "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
                         "executed": 3 * tflops, "traffic": None,
                         "peak_source": ("measured" if peaks else "fallback") + " dense bf16 burst / 2 (kind::tf32 runs at half the bf16 rate)",
                         "note": "per GPU; achieved = algorithmic FLOPs of a training step (1 062 912 per window: forward, dX and dW of "
                                 "every layer, each product once) / step time; the 3xTF32 split executes 3x that on the tensor pipe "
-                                "(`executed`); the step is latency-bound: 11 dependent launches of 4096-row GEMMs (DESIGN.md 6)"},
+                                "(`executed`); the step is latency-bound: %d dependent launches of 4096-row GEMMs per step (DESIGN.md 6)"
+                                % round(runs[best]["launches"] / max(1, steps))},
            "workload": "configs[2]: 1M cached windows, 100 speakers, batch 4096 per GPU, 1 epoch, lr 0.01, dropout 0.2"}
     # end to end through the host API: features and labels start in pinned host memory, are uploaded inside the timed region
     # (szb_memcpy_h2d), the epoch runs, the loss comes back (szb_net_train_epoch_dev returns it on the host)
