@@ -278,7 +278,9 @@ int32_t szb_comm_world(const szb_ctx* ctx);
  * posted peer stores and flag rounds -- no NCCL call inside a step.  enable: 0 = off (NCCL all-reduces),
  * 1 = on, protocol chosen by size; 2 = on, ONE-SHOT (every rank stores its whole vector into every peer, one flag round,
  * every rank adds the vectors in rank order while it updates); 3 = on, TWO-SHOT (scatter slices, owner reduces in rank order
- * and broadcasts, two flag rounds).  Replicas stay bit-identical with either.  *active reports whether the mapping succeeded
+ * and broadcasts, two flag rounds); 4 = on, PACKETS (one-shot, every element travels as an 8-byte {value, step} packet that is
+ * its own flag: no flag round, twice the bytes; tensor-core update kernel only, otherwise chosen by size).  Replicas stay
+ * bit-identical with all of them.  *active reports whether the mapping succeeded
  * on all ranks (otherwise every rank stays on NCCL). */
 szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active);
 

@@ -108,10 +108,10 @@ class Context:
 
 def _ctx_peer_exchange(self, enable, mode: str = "auto") -> bool:
     """Collective: switch the gradient exchange between NCCL all-reduces (default) and the all-reduce over NVLink peer memory
-    fused into the update kernel (include/streamz_b200.h, szb_comm_peer_exchange); mode "auto" | "one-shot" | "two-shot".
+    fused into the update kernel (include/streamz_b200.h, szb_comm_peer_exchange); mode "auto" | "one-shot" | "two-shot" | "ll" (one-shot with the flag inside every 8-byte packet).
     Returns whether the peer exchange is active."""
     active = C.c_int32()
-    code = {"auto": 1, "one-shot": 2, "two-shot": 3}[mode] if enable else 0
+    code = {"auto": 1, "one-shot": 2, "two-shot": 3, "ll": 4}[mode] if enable else 0
     N.check(N.lib.szb_comm_peer_exchange(self.handle, code, C.byref(active)))
     return bool(active.value)
 

@@ -152,10 +152,14 @@ szb_status szb_ctx_create(int32_t device, void* stream, szb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SZB_NO_PDL")) ctx->pdl = !(e[0] == '1');
     if (const char* e = getenv("SZB_NO_GRAPHS")) ctx->graphs = !(e[0] == '1');
+    if (const char* e = getenv("SZB_GRAPH_MAX_ROWS")) ctx->graph_max_rows = std::max(0, atoi(e));
+    if (const char* e = getenv("SZB_GRAPH_PEERS")) ctx->graph_peers = (e[0] == '1');
     if (const char* e = getenv("SZB_NO_SMALL_KERNEL")) ctx->small_steps = !(e[0] == '1');
     if (const char* e = getenv("SZB_GEMM_TA")) ctx->gemm_ta = (e[0] == '1');
     if (const char* e = getenv("SZB_STEP_FUSE")) ctx->step_fuse = atoi(e) & 7;
     if (const char* e = getenv("SZB_GEMM_TMA")) ctx->gemm_tma = (e[0] == '1');
+    if (const char* e = getenv("SZB_P2P_EARLY_PUSH")) ctx->p2p_early_push = (e[0] == '1');
+    if (const char* e = getenv("SZB_P2P_LL")) ctx->p2p_ll_auto = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_CHUNK_MB")) ctx->l2_chunk_mb = std::max(0, atoi(e));
     if (const char* e = getenv("SZB_FUSED_RESAMPLE")) ctx->fuse_resample = (e[0] == '1');
     if (const char* e = getenv("SZB_L2_STREAMS")) ctx->l2_streams = atoi(e) > 1 ? 2 : 1;

@@ -163,8 +163,8 @@ static szb_status p2p_setup(szb_ctx* ctx) {
         p2p_teardown(ctx);
         return SZB_OK;
     }
-    SZB_TRY(ctx->p2p_counters.reserve(128));            // [0, 8): tickets; [64, 128): phase trace (8 x u64)
-    SZB_CUDA(cudaMemset(ctx->p2p_counters.ptr, 0, 128));
+    SZB_TRY(ctx->p2p_counters.reserve(1280));           // [0, 8): tickets; [64, 128): phase trace (8 x u64); [256, 1280): per-tile tickets of
+    SZB_CUDA(cudaMemset(ctx->p2p_counters.ptr, 0, 1280));  // the grouped weight-gradient launch (early push, gemm_tma.cuh)
     ctx->p2p_on = true;
     ctx->p2p_cap = kP2pCapFloats;
     ctx->p2p_step = 0;
@@ -201,7 +201,7 @@ szb_status szb_comm_init(szb_ctx* ctx, const uint8_t id[128], int32_t rank, int3
 
 szb_status szb_comm_peer_exchange(szb_ctx* ctx, int32_t enable, int32_t* active) {
     SZB_REQUIRE(ctx, "szb_comm_peer_exchange: ctx is NULL");
-    if (enable >= 1 && enable <= 3) ctx->p2p_mode = enable == 1 ? 0 : enable - 1;      // 1: choose by size, 2: one-shot, 3: two-shot
+    if (enable >= 1 && enable <= 4) ctx->p2p_mode = enable == 1 ? 0 : enable - 1;      // 1: choose by size, 2: one-shot, 3: two-shot, 4: packets
     if (ctx->world > 1 && ctx->nccl_comm) {
         SZB_CUDA(cudaSetDevice(ctx->device));
         if (enable && !ctx->p2p_on) SZB_TRY(p2p_setup(ctx));

@@ -83,6 +83,10 @@ struct szb_ctx {
     uint64_t launches = 0;
     uint64_t graph_launches = 0;   // cudaGraphLaunch calls (captured two-step training graphs)
     bool small_steps = true;   // epochs whose batches have <= 32 rows run as one persistent cooperative kernel (SZB_NO_SMALL_KERNEL=1: off)
+    int graph_max_rows = 1 << 30;   // largest batch whose epoch replays the captured two-step graph (SZB_GRAPH_MAX_ROWS); round 2 stopped at
+                                    // 256 rows -- large batches gain little on an idle host (77.4 vs 79.0 us per batch-4096 step) but no longer
+                                    // depend on the host keeping up with nine launches per 80 us (bench.py runs next to its clock sampler)
+    bool graph_peers = true;    // ... also in multi-GPU steps with the peer-memory exchange (SZB_GRAPH_PEERS=0: single GPU only)
     bool graphs = true;   // small-batch training epochs replay a captured two-step CUDA graph (SZB_NO_GRAPHS=1 turns it off)
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
     // Launch structure of a tensor-core training step (SZB_STEP_FUSE=<bits>, default 4; 0 = eleven launches per step: batch
@@ -141,7 +145,14 @@ struct szb_ctx {
     uint32_t* p2p_flags[kMaxPeers] = {};      // flag block of every rank: [s] / [16 + s] = last step rank s finished phase 0 / 1 for
     szb::DevBuf p2p_counters;                 // private last-CTA tickets of the two phases
     int p2p_max_blocks = 0;                   // co-resident CTA capacity of the update kernels (0 = not queried yet)
-    int p2p_mode = 0;                         // 0 = by size (one-shot below 6 MB of outgoing copies per step), 1 = one-shot, 2 = two-shot
+    int p2p_mode = 0;                         // 0 = by size (one-shot below 6 MB of outgoing copies per step), 1 = one-shot, 2 = two-shot,
+                                              // 3 = one-shot with the flag inside every 8-byte packet (no flag round; tensor-core path)
+    bool p2p_ll_auto = false;                 // mode 0 prefers the packet protocol when the vector fits (SZB_P2P_LL=1).  Measured at N = 2: 101.9 us
+                                              // per step against 102.6 us for the one-shot exchange with its flag round -- what an exchange costs
+                                              // is the time until the peer's data is visible, with or without flags; off (twice the bytes at N = 8)
+    bool p2p_early_push = false;              // one-shot exchange: finished gradient tiles are stored into the peers by the grouped weight-gradient
+                                              // launch instead of the update kernel (SZB_P2P_EARLY_PUSH=1).  Measured at N = 2: 102.5 us per step
+                                              // against 100.5 us without -- the flag round, not the data, is what the exchange costs; off
     bool p2p_trace_on = false;                // szb_comm_peer_trace: CTA 0 of the update kernel records its phase times
     void* p2p_region = nullptr;               // local allocation backing p2p_flags / p2p_inbox / p2p_red of this rank
 };

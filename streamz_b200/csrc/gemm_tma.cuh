@@ -375,12 +375,27 @@ __global__ void __launch_bounds__(kTmaThreads) gemm_tma_kernel(const GemmArgs g,
 }
 
 // Several independent products in one launch (see gemm_tc_ta_group_kernel).
+// Multi-GPU, one-shot gradient exchange (mlp.cu: p2p_exchange): the CTA that completes a gradient tile -- the last of its K
+// ranges to have added its partial sums -- stores the finished tile into this rank's slot on every peer right away, while the
+// other tiles are still being computed.  The update kernel then has nothing left to send but the [n_used, loss] tail, and its
+// system-scope fence no longer waits for 753 KB of posted NVLink stores per peer.
+constexpr int kMaxPushPeers = 16;
+constexpr int kMaxPushTiles = 256;
+struct PeerPush {
+    float* area[kMaxPushPeers];          // exchange area of every rank (this rank's own entry is not written)
+    unsigned long long slot_off;         // floats: ((step & 1) * world + rank) * cap -- this rank's slot of the step
+    const float* G;                      // the private gradient vector the products accumulate into
+    unsigned int* counters;              // [kMaxPushTiles] tickets, zero between launches
+    int world, rank;                     // world <= 1: no push
+};
 struct GroupArgsTma {
     GemmArgs g[kMaxGroup];
     CUtensorMap tmA[kMaxGroup], tmB[kMaxGroup];
     int first[kMaxGroup + 1];
     int tiles_n[kMaxGroup], tiles_m[kMaxGroup];
+    int nz[kMaxGroup], tile_first[kMaxGroup];       // K ranges per tile; index of the problem's first tile ticket
     int count;
+    PeerPush push;
 };
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(kTmaThreads) gemm_tma_group_kernel(const __grid_constant__ GroupArgsTma ga) {
@@ -391,7 +406,36 @@ __global__ void __launch_bounds__(kTmaThreads) gemm_tma_group_kernel(const __gri
         if (i < ga.count && b >= ga.first[i]) p = i;
     const int local = b - ga.first[p];
     const int tn = ga.tiles_n[p], tm = ga.tiles_m[p];
-    gemm_tma_body<BN, PASSES, EPI>(ga.g[p], &ga.tmA[p], &ga.tmB[p], local % tn, (local / tn) % tm, local / (tn * tm));
+    const int bx = local % tn, by = (local / tn) % tm;
+    gemm_tma_body<BN, PASSES, EPI>(ga.g[p], &ga.tmA[p], &ga.tmB[p], bx, by, local / (tn * tm));
+    if (ga.push.world > 1) {
+        // every thread of the CTA has issued its reductions (the body ends with a block barrier).  Release pattern as in
+        // p2p_publish: barrier -> fence -> ticket; the last K range of the tile then reads the finished sums from L2.
+        __shared__ int s_last;
+        const int tile = ga.tile_first[p] + by * tn + bx;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int ticket = atomicAdd(ga.push.counters + tile, 1u);
+            s_last = ticket == unsigned(ga.nz[p]) - 1u;
+            if (s_last) ga.push.counters[tile] = 0u;               // the next step finds it zero
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const GemmArgs& g = ga.g[p];
+            const int m0 = by * BM, n0 = bx * BN;
+            const int rows = min(BM, g.M - m0), nc4 = min(BN, g.N - n0) >> 2;      // launcher: N % 4 == 0, 16-byte aligned rows
+            const size_t base = size_t(g.C - ga.push.G) + size_t(m0) * g.ldc + n0;
+            for (int e = threadIdx.x; e < rows * nc4; e += blockDim.x) {
+                const int r = e / nc4, c4 = e - r * nc4;
+                const size_t idx = base + size_t(r) * g.ldc + 4 * c4;
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(ga.push.G + idx));
+#pragma unroll
+                for (int q = 0; q < kMaxPushPeers; ++q)
+                    if (q < ga.push.world && q != ga.push.rank) *reinterpret_cast<float4*>(ga.push.area[q] + ga.push.slot_off + idx) = v;
+            }
+        }
+    }
 }
 
 // ---- host side: tensor maps ---------------------------------------------------------------------------------------------
@@ -489,8 +533,11 @@ szb_status launch_gemm_tma_softmax(szb_ctx* ctx, GemmArgs g, bool* done) {
     return SZB_OK;
 }
 
+// push (optional): early peer push of the finished tiles; *pushed tells whether the launch does it (needs 16-byte aligned rows
+// of every C and N % 4 == 0, and few enough tiles for the ticket array).
 template <int PASSES>
-szb_status launch_gemm_tma_group(szb_ctx* ctx, const GemmArgs* gs, int count, bool* done) {
+szb_status launch_gemm_tma_group(szb_ctx* ctx, const GemmArgs* gs, int count, bool* done, const PeerPush* push = nullptr, bool* pushed = nullptr) {
+    if (pushed) *pushed = false;
     constexpr int BN = 128;
     *done = false;
     if (count < 1 || count > kMaxGroup || !ctx->gemm_tma) return SZB_OK;
@@ -513,10 +560,26 @@ szb_status launch_gemm_tma_group(szb_ctx* ctx, const GemmArgs* gs, int count, bo
         ga.g[p].k_chunk = ((kb_total + sp - 1) / sp) * BK;
         const int nz = (gs[p].K + ga.g[p].k_chunk - 1) / ga.g[p].k_chunk;      // every K range is non-empty
         ga.first[p] = ctas;
+        ga.nz[p] = nz;
         ctas += ga.tiles_n[p] * ga.tiles_m[p] * nz;
     }
     for (int p = count; p <= kMaxGroup; ++p) ga.first[p] = ctas;
     ga.count = count;
+    ga.push.world = 1;
+    if (push && push->world > 1 && push->world <= kMaxPushPeers) {
+        bool ok = true;
+        int tiles = 0;
+        for (int p = 0; p < count; ++p) {
+            ga.tile_first[p] = tiles;
+            tiles += ga.tiles_n[p] * ga.tiles_m[p];
+            const size_t off = size_t(gs[p].C - push->G);
+            ok = ok && gs[p].N % 4 == 0 && gs[p].ldc % 4 == 0 && off % 4 == 0 && (reinterpret_cast<uintptr_t>(push->G) & 15) == 0;
+        }
+        if (ok && tiles <= kMaxPushTiles && (push->slot_off % 4) == 0) {
+            ga.push = *push;
+            if (pushed) *pushed = true;
+        }
+    }
     using SL = SmemLayoutTma<BN, PASSES>;
     static bool attr_set[64] = {};
     if (!attr_set[ctx->device & 63]) {

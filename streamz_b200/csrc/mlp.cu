@@ -356,7 +356,7 @@ __device__ __forceinline__ void prep_batch_block(const PrepArgs& a, const int bl
     }
 }
 
-__global__ void prep_batch_kernel(const __grid_constant__ PrepArgs a, const StepParams* __restrict__ sp) {
+__global__ void prep_batch_kernel(const __grid_constant__ PrepArgs a, StepParams* __restrict__ sp) {
     extern __shared__ float prep_tile[];   // [n_in][33] when use_tile
     tc::pdl_launch_dependents();
     tc::pdl_wait();
@@ -365,6 +365,8 @@ __global__ void prep_batch_kernel(const __grid_constant__ PrepArgs a, const Step
     if (sp) {                              // captured step: position in the shuffled order and dropout key come from device memory
         perm += sp->cursor;
         key = sp->key;
+        // multi-GPU: the flag value of this step's gradient exchange (read by the update kernel, the last kernel of the step)
+        if (blockIdx.x == 0 && threadIdx.x == 0) sp->p2p_step += 1u;
     }
     if (a.blocks_per_step > 0) {
         // several steps of the epoch in one launch (szb_net_train_epoch_steps_dev: large batches): the batch kernel leaves the
@@ -418,7 +420,8 @@ struct P2pArgs {
     float* red[szb_ctx::kMaxPeers];          // two-shot: reduced-vector buffer of every rank
     float* area[szb_ctx::kMaxPeers];         // one-shot: [2 (step parity)][world (source rank)][cap] full gradient vectors
     size_t cap;                              // floats per vector slot of `area`
-    int one_shot;                            // 1: every rank stores its WHOLE vector into every peer (one flag round)
+    int one_shot;                            // 1: every rank stores its WHOLE vector into every peer (one flag round); 2: the same with
+                                             // the flag inside every 8-byte packet (no flag round at all: ll_send / ll_recv below)
     uint32_t* flags[szb_ctx::kMaxPeers];     // flag block of every rank: [0, 16) flag1 per source rank, [16, 32) flag2
     unsigned int* counters;                  // private: [0] CTAs done with phase 0, [1] with phase 1 (last-CTA detection)
     unsigned long long* trace;               // optional (szb_comm_peer_trace): CTA 0 accumulates %globaltimer deltas per phase
@@ -426,7 +429,8 @@ struct P2pArgs {
     uint32_t step;
     uint32_t n4, slice_g;                    // 16-byte groups in V, groups per slice
     int nblk;                                // CTAs taking part in the exchange: blocks [0, nblk) of the grid (0 = the whole grid)
-};
+    uint32_t sent4;                          // one-shot: 16-byte groups [0, sent4) were already stored into the peers by the grouped
+};                                           // weight-gradient launch (gemm_tma.cuh: PeerPush); the update kernel sends the rest
 
 __device__ __forceinline__ void p2p_wait_flags(const uint32_t* f, int world, uint32_t step) {
     if (int(threadIdx.x) < world) {
@@ -451,7 +455,7 @@ __device__ __forceinline__ void p2p_wait_flags(const uint32_t* f, int world, uin
 // Called by every thread of every CTA when this CTA's stores of a phase are issued: the LAST CTA of the grid to arrive
 // publishes `step` into flag word (base + rank) of every peer.  (stores -> bar -> fence.sys -> ticket) is the release
 // pattern, (ticket -> fence.sys -> flag store.release) chains it to the peers' acquire loads.
-__device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* counter, int flag_base) {
+__device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* counter, int flag_base, const uint32_t step) {
     __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -462,7 +466,7 @@ __device__ __forceinline__ void p2p_publish(const P2pArgs& a, unsigned int* coun
     }
     __syncthreads();
     if (s_last && int(threadIdx.x) < a.world)      // (the release store orders everything the barrier above made visible to this thread)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + flag_base + a.rank), "r"(a.step) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + flag_base + a.rank), "r"(step) : "memory");
 }
 
 // Phases 0 and 1.  On return (all threads of the CTA) the local `red` buffer holds the rank-ordered sum of every rank's
@@ -476,7 +480,7 @@ __device__ __forceinline__ unsigned long long p2p_now() {
 // 3 reduce + broadcast, 4 publish, 5 wait flag2); slot 7 counts the steps
 #define P2P_TRACE(i) do { if (tr) { const unsigned long long tn = p2p_now(); atomicAdd(a.trace + (i), tn - t_prev); t_prev = tn; } } while (0)
 
-__device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const float* __restrict__ G) {
+__device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const float* __restrict__ G, const uint32_t step) {
     const int me = a.rank, W = a.world;
     const bool tr = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long t_prev = tr ? p2p_now() : 0ull;
@@ -488,17 +492,17 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
         // but saves a whole publish / wait round (~12 us): the faster exchange while the vector is small against the link
         // (753 KB x 7 peers = 7 us of NVLink time at W = 8).  Slots alternate by step parity: a rank overwrites slot p two steps
         // later, after every peer has published the step in between, i.e. has finished the update that read slot p.
-        const size_t slot4 = (size_t(a.step & 1u) * W + me) * (a.cap / 4);
-        for (size_t i = t0; i < a.n4; i += nthreads) {
+        const size_t slot4 = (size_t(step & 1u) * W + me) * (a.cap / 4);
+        for (size_t i = a.sent4 + t0; i < a.n4; i += nthreads) {
             const float4 v = G4[i];
 #pragma unroll
             for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
                 if (r < W && r != me) reinterpret_cast<float4*>(a.area[r])[slot4 + i] = v;
         }
         P2P_TRACE(0);
-        p2p_publish(a, a.counters + 0, 0);
+        p2p_publish(a, a.counters + 0, 0, step);
         P2P_TRACE(1);
-        p2p_wait_flags(a.flags[me], W, a.step);
+        p2p_wait_flags(a.flags[me], W, step);
         P2P_TRACE(2);
         if (tr) atomicAdd(a.trace + 7, 1ull);
         return nullptr;
@@ -511,10 +515,10 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
         reinterpret_cast<float4*>(a.inbox[d])[size_t(me) * a.slice_g + (i - size_t(d) * a.slice_g)] = v;
     }
     P2P_TRACE(0);
-    p2p_publish(a, a.counters + 0, 0);
+    p2p_publish(a, a.counters + 0, 0, step);
     P2P_TRACE(1);
     // ---- phase 1: reduce my slice in rank order, broadcast it
-    p2p_wait_flags(a.flags[me], W, a.step);
+    p2p_wait_flags(a.flags[me], W, step);
     P2P_TRACE(2);
     const size_t g0 = size_t(me) * a.slice_g;
     const size_t mine = g0 < a.n4 ? min(size_t(a.slice_g), size_t(a.n4) - g0) : 0;
@@ -533,10 +537,10 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
             if (r < W) reinterpret_cast<float4*>(a.red[r])[g0 + o] = s;
     }
     P2P_TRACE(3);
-    p2p_publish(a, a.counters + 1, 16);
+    p2p_publish(a, a.counters + 1, 16, step);
     P2P_TRACE(4);
     // ---- phase 2 entry: everybody's reduced slice has landed here
-    p2p_wait_flags(a.flags[me] + 16, W, a.step);
+    p2p_wait_flags(a.flags[me] + 16, W, step);
     P2P_TRACE(5);
     if (tr) atomicAdd(a.trace + 7, 1ull);
     return a.red[me];
@@ -544,9 +548,9 @@ __device__ __forceinline__ const float* p2p_exchange(const P2pArgs& a, const flo
 
 // Element idx of the step's reduced gradient after p2p_exchange: the two-shot exchange left it in R; after the one-shot
 // exchange it is the rank-ordered sum of this rank's private value and the peers' copies in the local area.
-__device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __restrict__ R, const float* __restrict__ G, size_t idx) {
+__device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __restrict__ R, const float* __restrict__ G, size_t idx, const uint32_t step) {
     if (!a.one_shot) return __ldcg(R + idx);
-    const float* base = a.area[a.rank] + size_t(a.step & 1u) * a.world * a.cap + idx;
+    const float* base = a.area[a.rank] + size_t(step & 1u) * a.world * a.cap + idx;
     float v[szb_ctx::kMaxPeers];
 #pragma unroll
     for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
@@ -555,6 +559,54 @@ __device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __re
 #pragma unroll
     for (int r = 1; r < szb_ctx::kMaxPeers; ++r)
         if (r < a.world) s += v[r];
+    return s;
+}
+
+// ---- one-shot exchange without a flag round ("LL": the protocol NCCL uses for small messages) -----------------------------
+// A flag round costs ~12 us (block barrier, system-scope fence = the acknowledgement round trip of the posted NVLink stores,
+// ticket, release store, propagation, the peers' acquire polls) against ~1.5 us of data movement (szb_comm_peer_trace), and
+// sending the data earlier does not shorten it (PeerPush, measured).  So the data carries its own flag: element idx of the
+// step's vector travels as ONE 8-byte packet {value, step}; an aligned 8-byte store is performed as a whole, so a receiver
+// that reads the packet with one 8-byte load and finds the step number has the value that belongs to it.  No fence, no
+// ticket, no flag, no CTA waits for another CTA of its own grid: every thread sends the elements it will update, then polls
+// the peers' packets of exactly those elements and adds them in rank order (replicas stay bit-identical, and equal to the
+// other two protocols bit for bit).  Costs twice the bytes; slots alternate by step parity exactly as in the one-shot exchange
+// (a slot is rewritten two steps later, after every peer has sent the step in between, i.e. finished the update that read it).
+__device__ __forceinline__ unsigned long long* ll_slot(const P2pArgs& a, int dst, int src, const uint32_t step) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(a.area[dst]) +
+                                                 (size_t(step & 1u) * size_t(a.world) + size_t(src)) * a.cap * sizeof(float));
+}
+__device__ __forceinline__ void ll_send(const P2pArgs& a, size_t idx, float v, const uint32_t step) {
+    const uint32_t bits = __float_as_uint(v);
+#pragma unroll
+    for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+        if (r < a.world && r != a.rank)
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(ll_slot(a, r, a.rank, step) + idx), "r"(bits), "r"(step) : "memory");
+}
+__device__ __forceinline__ float ll_recv(const P2pArgs& a, int src, size_t idx, const uint32_t step) {
+    const unsigned long long* p = ll_slot(a, a.rank, src, step) + idx;
+    uint32_t bits = 0, flag = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(flag) : "l"(p) : "memory");
+        if (flag == step) break;
+        if ((spin & 0xFFFFu) == 0xFFFFu) {                 // a peer that is minutes late has died: never hang the GPU
+            const unsigned long long t = p2p_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 180ull * 1000000000ull) __trap();
+        }
+    }
+    return __uint_as_float(bits);
+}
+// rank-ordered sum of element idx over all ranks: this rank's value from its private gradient, the others from their packets
+__device__ __forceinline__ float ll_grad_at(const P2pArgs& a, const float* __restrict__ G, size_t idx, const uint32_t step) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < szb_ctx::kMaxPeers; ++r)
+        if (r < a.world) {
+            const float v = r == a.rank ? G[idx] : ll_recv(a, r, idx, step);
+            s = r == 0 ? v : s + v;
+        }
     return s;
 }
 
@@ -580,8 +632,82 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
         if (blockIdx.x == 0 && threadIdx.x == 0) sp->cursor += uint32_t(advance);
     }
     const bool peers = a.world > 1;
-    const float* R = peers ? p2p_exchange(a, G) : G;     // the step's (reduced) gradient vector
-    auto grad_at = [&](size_t idx) -> float { return peers ? p2p_grad_at(a, R, G, idx) : R[idx]; };
+    // the step's flag value: from the launch, or -- in a captured step, whose parameters are frozen -- from device memory, where the
+    // step's batch kernel has just counted it up
+    const uint32_t step = sp ? sp->p2p_step : a.step;
+    const int t1 = ((n_in + 31) / 32) * ((h1 + 31) / 32), t2 = ((h1 + 31) / 32) * ((h2 + 31) / 32),
+              t3 = ((h2 + 31) / 32) * ((n_out + 31) / 32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t nb = size_t(h1) + h2 + n_out;
+    const int nblk_tiles = t1 + t2 + t3;
+    // biases: spread over the blocks starting behind the last tile's block
+    const size_t bt = size_t((int(blockIdx.x) + n_upd - (nblk_tiles % n_upd)) % n_upd) * blockDim.x + threadIdx.x;
+    auto tile_of = [&](int t, int& K, int& N, size_t& off_w, size_t& off_wt, int& k0, int& n0) {
+        int tt;
+        if (t < t1) { K = n_in; N = h1; tt = t; off_w = 0; off_wt = 0; }
+        else if (t < t1 + t2) { K = h1; N = h2; tt = t - t1; off_w = off_w2; off_wt = off_wt2; }
+        else { K = h2; N = n_out; tt = t - t1 - t2; off_w = off_w3; off_wt = off_wt3; }
+        const int ntn = (N + 31) / 32;
+        k0 = (tt / ntn) * 32; n0 = (tt % ntn) * 32;
+    };
+    auto bias_idx = [&](size_t i) -> size_t {
+        return i < size_t(h1) ? off_b1 + i : (i < size_t(h1) + h2 ? off_b2 + (i - h1) : off_b3 + (i - h1 - h2));
+    };
+    if (peers && a.one_shot == 2) {
+        // ---- exchange inside the packets (ll_send / ll_recv): pass 1 sends every element this thread will update, pass 2
+        // polls the peers' packets of the same elements.  The thread that sends an element is the one that zeroes it.
+        __shared__ float s_tail[2];
+        if (blockIdx.x == 0 && threadIdx.x < 8) ll_send(a, np + threadIdx.x, G[np + threadIdx.x], step);    // [n_used, loss] blocks first
+        for (int t = blockIdx.x; t < nblk_tiles; t += n_upd) {
+            int K, N, k0, n0; size_t off_w, off_wt;
+            tile_of(t, K, N, off_w, off_wt, k0, n0);
+#pragma unroll
+            for (int r = warp; r < 32; r += 8) {
+                const int k = k0 + r, n = n0 + lane;
+                if (k < K && n < N) { const size_t idx = off_w + size_t(k) * N + n; ll_send(a, idx, G[idx], step); }
+            }
+        }
+        for (size_t i = bt; i < nb; i += size_t(n_upd) * blockDim.x) { const size_t idx = bias_idx(i); ll_send(a, idx, G[idx], step); }
+        if (threadIdx.x < 2) s_tail[threadIdx.x] = ll_grad_at(a, G, np + 4 * parity + threadIdx.x, step);
+        __syncthreads();
+        const float n_used_ll = s_tail[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (stats) { stats[0] += double(s_tail[1]); stats[1] += double(n_used_ll); }
+            G[np + 4 * (1 - parity)] = 0.f;            // the next step's tail block (nobody reads it in this launch)
+            G[np + 4 * (1 - parity) + 1] = 0.f;
+        }
+        const float scale_ll = n_used_ll > 0.f ? lr / n_used_ll : 0.f;
+        for (int t = blockIdx.x; t < nblk_tiles; t += n_upd) {
+            int K, N, k0, n0; size_t off_w, off_wt;
+            tile_of(t, K, N, off_w, off_wt, k0, n0);
+            __syncthreads();
+#pragma unroll
+            for (int r = warp; r < 32; r += 8) {
+                const int k = k0 + r, n = n0 + lane;
+                if (k < K && n < N) {
+                    const size_t idx = off_w + size_t(k) * N + n;
+                    const float p = P[idx] - ll_grad_at(a, G, idx, step) * scale_ll;
+                    P[idx] = p;
+                    G[idx] = 0.f;
+                    tile[r][lane] = p;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = warp; r < 32; r += 8) {
+                const int n = n0 + r, k = k0 + lane;
+                if (n < N && k < K) WT[off_wt + size_t(n) * K + k] = tile[lane][r];
+            }
+        }
+        for (size_t i = bt; i < nb; i += size_t(n_upd) * blockDim.x) {
+            const size_t idx = bias_idx(i);
+            P[idx] -= ll_grad_at(a, G, idx, step) * scale_ll;
+            G[idx] = 0.f;
+        }
+        return;
+    }
+    const float* R = peers ? p2p_exchange(a, G, step) : G;     // the step's (reduced) gradient vector
+    auto grad_at = [&](size_t idx) -> float { return peers ? p2p_grad_at(a, R, G, idx, step) : R[idx]; };
     const float n_used = grad_at(np + 4 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (stats) {
@@ -594,17 +720,10 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
         G[np + 4 * (1 - parity) + 1] = 0.f;
     }
     const float scale = n_used > 0.f ? lr / n_used : 0.f;   // empty batch: gradients are zero, nothing moves (lib.rs:1003-1005)
-    const int t1 = ((n_in + 31) / 32) * ((h1 + 31) / 32), t2 = ((h1 + 31) / 32) * ((h2 + 31) / 32),
-              t3 = ((h2 + 31) / 32) * ((n_out + 31) / 32);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = blockIdx.x; t < t1 + t2 + t3; t += n_upd) {
-        int K, N, tt;
+    for (int t = blockIdx.x; t < nblk_tiles; t += n_upd) {
+        int K, N, k0, n0;
         size_t off_w, off_wt;
-        if (t < t1) { K = n_in; N = h1; tt = t; off_w = 0; off_wt = 0; }
-        else if (t < t1 + t2) { K = h1; N = h2; tt = t - t1; off_w = off_w2; off_wt = off_wt2; }
-        else { K = h2; N = n_out; tt = t - t1 - t2; off_w = off_w3; off_wt = off_wt3; }
-        const int ntn = (N + 31) / 32;
-        const int k0 = (tt / ntn) * 32, n0 = (tt % ntn) * 32;
+        tile_of(t, K, N, off_w, off_wt, k0, n0);
         __syncthreads();                                  // the previous tile of this block has been read out
 #pragma unroll
         for (int r = warp; r < 32; r += 8) {
@@ -624,12 +743,8 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
             if (n < N && k < K) WT[off_wt + size_t(n) * K + k] = tile[lane][r];
         }
     }
-    const size_t nb = size_t(h1) + h2 + n_out;
-    const int nblk_tiles = t1 + t2 + t3;
-    // biases: spread over the blocks starting behind the last tile's block
-    const size_t bt = size_t((int(blockIdx.x) + n_upd - (nblk_tiles % n_upd)) % n_upd) * blockDim.x + threadIdx.x;
     for (size_t i = bt; i < nb; i += size_t(n_upd) * blockDim.x) {
-        const size_t idx = i < size_t(h1) ? off_b1 + i : (i < size_t(h1) + h2 ? off_b2 + (i - h1) : off_b3 + (i - h1 - h2));
+        const size_t idx = bias_idx(i);
         P[idx] -= grad_at(idx) * scale;
         G[idx] = 0.f;
     }
@@ -638,8 +753,8 @@ __global__ void __launch_bounds__(256) sgd_fused_kernel(float* __restrict__ P, f
 // FP32 (CUDA-core) path of a multi-GPU step: the same exchange, then the plain update theta -= (lr / sum n_used) * sum g.
 __global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params, const float* __restrict__ G,
                                                       const __grid_constant__ P2pArgs a, size_t n, float lr, double* __restrict__ stats) {
-    const float* R = p2p_exchange(a, G);
-    const float n_used = p2p_grad_at(a, R, G, n), loss = p2p_grad_at(a, R, G, n + 1);
+    const float* R = p2p_exchange(a, G, a.step);
+    const float n_used = p2p_grad_at(a, R, G, n, a.step), loss = p2p_grad_at(a, R, G, n + 1, a.step);
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
         stats[0] += double(loss);
         stats[1] += double(n_used);
@@ -647,7 +762,7 @@ __global__ void __launch_bounds__(256) sgd_p2p_kernel(float* __restrict__ params
     if (n_used <= 0.f) return;             // empty global batch: no-op (lib.rs:1003-1005)
     const float scale = lr / n_used;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
-        params[i] -= p2p_grad_at(a, R, G, i) * scale;
+        params[i] -= p2p_grad_at(a, R, G, i, a.step) * scale;
 }
 
 __global__ void init_uniform_kernel(float* __restrict__ w, size_t n, unsigned long long key, unsigned long long base) {
@@ -917,6 +1032,38 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
         net->tail_parity = 0;
     }
     net->grads_zero = false;
+    P2pArgs a{};
+    a.world = 1;
+    int p2p_blocks = 0;
+    if (p2p) {
+        const size_t nv = np + kGradTail;
+        a.n4 = uint32_t((nv + 3) / 4);
+        a.slice_g = (a.n4 + uint32_t(ctx->world) - 1) / uint32_t(ctx->world);
+        for (int r = 0; r < ctx->world; ++r) {
+            a.inbox[r] = ctx->p2p_inbox[r];
+            a.red[r] = ctx->p2p_red[r];
+            a.area[r] = ctx->p2p_inbox[r];
+            a.flags[r] = ctx->p2p_flags[r];
+        }
+        a.cap = ctx->p2p_cap;
+        // one round of flags instead of two while (world - 1) copies of the vector are a few microseconds of NVLink time
+        a.one_shot = ctx->p2p_mode == 1 || (ctx->p2p_mode != 2 && size_t(ctx->world - 1) * nv * sizeof(float) <= (size_t(6) << 20)) ? 1 : 0;
+        // flag inside the packets (no flag round): tensor-core update kernel only; a packet slot holds cap / 2 elements
+        if ((ctx->p2p_mode == 3 || (ctx->p2p_mode == 0 && ctx->p2p_ll_auto)) && net->precision != 0 && 2 * nv <= ctx->p2p_cap &&
+            size_t(ctx->world - 1) * nv * 8 <= (size_t(32) << 20))
+            a.one_shot = 2;
+        a.counters = ctx->p2p_counters.as<unsigned int>();
+        a.trace = ctx->p2p_trace_on ? reinterpret_cast<unsigned long long*>(ctx->p2p_counters.as<unsigned char>() + 64) : nullptr;
+        a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
+        // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
+        if (ctx->p2p_max_blocks == 0) {
+            int per_sm_fused = 0, per_sm_plain = 0;
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 0));
+            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_plain, sgd_p2p_kernel, 256, 0));
+            ctx->p2p_max_blocks = std::max(1, std::min(per_sm_fused, per_sm_plain)) * ctx->sm_count;
+        }
+        p2p_blocks = ctx->p2p_max_blocks;
+    }
     bool reduced = p2p;     // gradient slices already all-reduced (overlapped) inside the backward pass, or exchanged below
     if (B > 0) {
         const BatchView own{net->xb.as<float>(), net->xbT.as<float>(), net->lab.as<uint32_t>(), net->valid.as<uint8_t>()};
@@ -962,8 +1109,20 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
                 // layer's all-reduce overlaps the GEMMs of the layers before it.)
                 SZB_TRY(gemm_tc<tc::TC_MUL_DTANH>(net, gx2));
                 SZB_TRY(gemm_tc<tc::TC_MUL_DRELU>(net, gx1));
-                if (net->precision == 2) SZB_TRY(tc::launch_gemm_tma_group<1>(ctx, gw, 3, &grouped));
-                else SZB_TRY(tc::launch_gemm_tma_group<3>(ctx, gw, 3, &grouped));
+                // one-shot peer exchange: the launch also stores every finished gradient tile into the peers (PeerPush)
+                tc::PeerPush push{};
+                bool pushed = false;
+                if (p2p && a.one_shot && ctx->p2p_early_push) {
+                    for (int r = 0; r < ctx->world; ++r) push.area[r] = a.area[r];
+                    push.slot_off = (size_t(a.step & 1u) * size_t(a.world) + size_t(a.rank)) * (a.cap / 4) * 4;
+                    push.G = G;
+                    push.counters = ctx->p2p_counters.as<unsigned int>() + 64;
+                    push.world = a.world; push.rank = a.rank;
+                }
+                if (net->precision == 2) SZB_TRY(tc::launch_gemm_tma_group<1>(ctx, gw, 3, &grouped, &push, &pushed));
+                else SZB_TRY(tc::launch_gemm_tma_group<3>(ctx, gw, 3, &grouped, &push, &pushed));
+                if (pushed) a.sent4 = uint32_t(np / 4);       // [0, np) = the three products' outputs; the tail (and the group that
+                                                              // straddles np) is still sent by the update kernel
                 if (!grouped) {
                     if (net->precision == 2) SZB_TRY(tc::launch_gemm_tc_group<1>(ctx, gw, 3, &grouped));
                     else SZB_TRY(tc::launch_gemm_tc_group<3>(ctx, gw, 3, &grouped));
@@ -1027,34 +1186,6 @@ static szb_status train_step_staged(szb_net* net, int B, const float* target_vec
             SZB_TRY(comm_allreduce_f32(ctx, G, np + kGradTail));
         }
     }
-    P2pArgs a{};
-    a.world = 1;
-    int p2p_blocks = 0;
-    if (p2p) {
-        const size_t nv = np + kGradTail;
-        a.n4 = uint32_t((nv + 3) / 4);
-        a.slice_g = (a.n4 + uint32_t(ctx->world) - 1) / uint32_t(ctx->world);
-        for (int r = 0; r < ctx->world; ++r) {
-            a.inbox[r] = ctx->p2p_inbox[r];
-            a.red[r] = ctx->p2p_red[r];
-            a.area[r] = ctx->p2p_inbox[r];
-            a.flags[r] = ctx->p2p_flags[r];
-        }
-        a.cap = ctx->p2p_cap;
-        // one round of flags instead of two while (world - 1) copies of the vector are a few microseconds of NVLink time
-        a.one_shot = ctx->p2p_mode == 1 || (ctx->p2p_mode == 0 && size_t(ctx->world - 1) * nv * sizeof(float) <= (size_t(6) << 20)) ? 1 : 0;
-        a.counters = ctx->p2p_counters.as<unsigned int>();
-        a.trace = ctx->p2p_trace_on ? reinterpret_cast<unsigned long long*>(ctx->p2p_counters.as<unsigned char>() + 64) : nullptr;
-        a.rank = ctx->rank; a.world = ctx->world; a.step = ++ctx->p2p_step;
-        // the exchange makes the CTAs of a launch wait for one another: the whole grid has to be resident
-        if (ctx->p2p_max_blocks == 0) {
-            int per_sm_fused = 0, per_sm_plain = 0;
-            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, sgd_fused_kernel, 256, 0));
-            SZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_plain, sgd_p2p_kernel, 256, 0));
-            ctx->p2p_max_blocks = std::max(1, std::min(per_sm_fused, per_sm_plain)) * ctx->sm_count;
-        }
-        p2p_blocks = ctx->p2p_max_blocks;
-    }
     if (fused) {
         SZB_TRY(net->wt.reserve(net->n_wt() * 4));
         const int tiles = int(((net->n_in + 31) / 32) * ((net->h1 + 31) / 32) + ((net->h1 + 31) / 32) * ((net->h2 + 31) / 32) +
@@ -1098,7 +1229,7 @@ static PrepArgs make_prep_args(szb_net* net, const float* d_feats, const uint32_
 }
 
 static szb_status launch_prep(szb_net* net, const float* d_feats, const uint32_t* d_labels, const uint32_t* d_perm, int B,
-                              const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key, const StepParams* sp = nullptr) {
+                              const uint8_t* d_keep, int keep_by_row, float prob, unsigned long long key, StepParams* sp = nullptr) {
     if (B <= 0) return SZB_OK;
     const int wpb = B >= 32 ? 32 : 8;     // one warp per row when the block's 32 rows exist: every gather load in flight at once
     size_t tile_bytes = 0;
@@ -1116,6 +1247,7 @@ static szb_status capture_step_graph(szb_net* net, const StepGraphKey& k, float 
     szb_ctx* ctx = net->ctx;
     if (net->step_graph) { cudaGraphExecDestroy(net->step_graph); net->step_graph = nullptr; }
     const uint64_t launches0 = ctx->launches;
+    const uint32_t p2p_step0 = ctx->p2p_step;           // a captured step takes its exchange step number from device memory
     StepParams* sp = net->step_params.as<StepParams>();
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); net->step_graph_failed = true; return SZB_OK; }
@@ -1128,6 +1260,7 @@ static szb_status capture_step_graph(szb_net* net, const StepGraphKey& k, float 
     const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
     net->step_graph_kernels = uint32_t(ctx->launches - launches0);   // kernels in one replay (two steps)
     ctx->launches = launches0;                          // nothing ran
+    ctx->p2p_step = p2p_step0;
     if (st != SZB_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&net->step_graph, graph, 0) != cudaSuccess) {
         cudaGetLastError();
         net->step_graph = nullptr;
@@ -1422,7 +1555,7 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
             a.xb = net->chunk_xb.as<float>(); a.xbT = net->chunk_xbT.as<float>(); a.lab = net->chunk_lab.as<uint32_t>();
             a.valid = net->chunk_valid.as<uint8_t>();
             a.blocks_per_step = int((B0 + 31) / 32);
-            SZB_CUDA(launch_pdl(ctx, prep_batch_kernel, dim3(cnt * a.blocks_per_step), dim3(1024), tile_bytes, a, static_cast<const StepParams*>(nullptr)));
+            SZB_CUDA(launch_pdl(ctx, prep_batch_kernel, dim3(cnt * a.blocks_per_step), dim3(1024), tile_bytes, a, static_cast<StepParams*>(nullptr)));
             ctx->launches += 1;
             for (uint32_t j = 0; j < cnt; ++j) {
                 const BatchView bv{a.xb + size_t(j) * B0 * ni, a.xbT + size_t(j) * B0 * (ni + 1), a.lab + size_t(j) * B0, a.valid + size_t(j) * B0};
@@ -1436,11 +1569,14 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
     const int B0 = int(step_sizes[0]);
     uint32_t n_full = 0;
     while (n_full < n_steps && int(step_sizes[n_full]) == B0) ++n_full;
-    if (ctx->graphs && ctx->world == 1 && net->precision != 0 && !net->step_graph_failed && B0 > 0 && B0 <= 256 && n_full >= 8) {
+    // multi-GPU: only with the peer-memory exchange (no collective call inside a step), and when the vector fits its buffers
+    const bool peers_ok = ctx->world == 1 || (ctx->p2p_on && ctx->graph_peers && net->n_params() + kGradTail + 4 * size_t(ctx->world) + 4 <= ctx->p2p_cap);
+    if (ctx->graphs && peers_ok && net->precision != 0 && !net->step_graph_failed && B0 > 0 && B0 <= ctx->graph_max_rows && n_full >= 8) {
         SZB_TRY(net->step_params.reserve(sizeof(StepParams)));
         StepGraphKey k;
         k.B = B0; k.precision = net->precision; k.feats = d_feats; k.labels = d_labels; k.keep = d_keep; k.perm = net->perm.ptr;
         k.params = net->params.ptr; k.prob = dropout; k.cap_rows = net->cap_rows; k.n_out = net->n_out;
+        k.exchange = ctx->world > 1 ? 1 + ctx->p2p_mode : 0;
         if (!net->grads_zero || net->wt_dirty) {       // the first steps of a net run plainly: they set up the state a captured step assumes
             SZB_TRY(plain_step());
             SZB_TRY(plain_step());
@@ -1453,12 +1589,13 @@ szb_status szb_net_train_epoch_steps_dev(szb_net* net, const float* d_feats, con
             const uint32_t n_pairs = (n_full - i) / 2;
             void* hp = nullptr;
             SZB_TRY(ctx->h_stage.acquire(sizeof(StepParams), &hp));
-            *static_cast<StepParams*>(hp) = StepParams{ uint32_t(s), lr, key };
+            *static_cast<StepParams*>(hp) = StepParams{ uint32_t(s), lr, key, ctx->p2p_step, 0u };
             SZB_CUDA(cudaMemcpyAsync(net->step_params.ptr, hp, sizeof(StepParams), cudaMemcpyHostToDevice, ctx->stream));
             SZB_TRY(ctx->h_stage.uploaded(ctx->stream));
             for (uint32_t p = 0; p < n_pairs; ++p) SZB_CUDA(cudaGraphLaunch(net->step_graph, ctx->stream));
             ctx->launches += uint64_t(n_pairs) * net->step_graph_kernels;   // 2 x (batch kernel, the step's GEMMs, [softmax,] update)
             ctx->graph_launches += n_pairs;
+            if (ctx->world > 1) ctx->p2p_step += 2 * n_pairs;      // the replayed steps counted it up in device memory
             i += 2 * n_pairs;
             s += uint64_t(2 * n_pairs) * uint64_t(B0);
         }

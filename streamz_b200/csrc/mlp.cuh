@@ -10,6 +10,8 @@ struct StepParams {
     uint32_t cursor;              // first row of the step in the epoch's permutation
     float lr;
     unsigned long long key;       // dropout key of the epoch (seed, stream)
+    uint32_t p2p_step;            // multi-GPU: gradient exchanges done so far; the batch kernel of a step counts it up, the update
+    uint32_t pad;                 // kernel uses it as the step's flag value (szb_ctx::p2p_step follows on the host)
 };
 struct StepGraphKey {             // everything a captured step bakes in
     int B = 0, precision = -1, parity = -1;
@@ -17,9 +19,10 @@ struct StepGraphKey {             // everything a captured step bakes in
     float prob = -1.f;
     uint64_t cap_rows = 0;
     uint32_t n_out = 0;
+    int exchange = 0;             // 0 = single GPU, 1 + szb_ctx::p2p_mode otherwise
     bool operator==(const StepGraphKey& o) const {
         return B == o.B && precision == o.precision && parity == o.parity && feats == o.feats && labels == o.labels && keep == o.keep &&
-               perm == o.perm && params == o.params && prob == o.prob && cap_rows == o.cap_rows && n_out == o.n_out;
+               perm == o.perm && params == o.params && prob == o.prob && cap_rows == o.cap_rows && n_out == o.n_out && exchange == o.exchange;
     }
 };
 }  // namespace szb

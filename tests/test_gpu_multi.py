@@ -1,5 +1,5 @@
 """2 / 4 / 8 ranks on as many GPUs (one process per GPU): batch-parallel training must reproduce the single-GPU epoch with
-either gradient exchange (NCCL all-reduces, or the two-shot peer-memory exchange fused into the update kernel) and leave
+any gradient exchange (NCCL all-reduces, or the one-shot / two-shot / packet peer-memory exchange fused into the update kernel) and leave
 bit-identical replicas; clip-sharded extraction must reproduce the single-GPU features.  A world size is skipped when
 fewer GPUs are visible (the driver's 1-GPU box skips all three; `gpurun --gpus 8` runs all three, log under profiles/)."""
 import os
@@ -41,9 +41,9 @@ def _worker(rank, world, port, tmp):
         tot += loss; cnt += used
     # the same two epochs again with the two-shot peer-memory exchange fused into the update kernel instead of NCCL,
     # on the tensor-core path (sgd_fused_kernel) and on the FP32 CUDA-core path (sgd_p2p_kernel)
-    w2, w3, w4 = None, None, None
+    w2, w3, w4, w6 = None, None, None, None
     peer = True
-    for mode, proto in (("3xtf32", "one-shot"), ("3xtf32", "two-shot"), ("fp32", "auto")):
+    for mode, proto in (("3xtf32", "one-shot"), ("3xtf32", "two-shot"), ("3xtf32", "ll"), ("fp32", "auto")):
         peer = ctx.comm_peer_exchange(True, proto) and peer
         net2 = sz.SimpleNeuralNet.from_weights(*[d[f"p{i}"] for i in range(6)], ctx=ctx).set_precision(mode)
         for epoch in range(2):
@@ -53,6 +53,8 @@ def _worker(rank, world, port, tmp):
             w2 = net2.weights()
         elif proto == "two-shot":
             w4 = net2.weights()
+        elif proto == "ll":
+            w6 = net2.weights()
         else:
             w3 = net2.weights()
     # large batches (264 rows per rank): the update kernel of a step also prepares the next step's batch with extra CTAs that
@@ -70,7 +72,7 @@ def _worker(rank, world, port, tmp):
     feats = sz.FeatureExtractor(ctx).extract_batch(clips[lo:hi]) if hi > lo else []
     np.savez(os.path.join(tmp, f"out{rank}.npz"), *net.weights(), peer=peer, **{f"q{i}": w for i, w in enumerate(w2)},
              **{f"r{i}": w for i, w in enumerate(w3)}, **{f"s{i}": w for i, w in enumerate(w4)},
-             **{f"t{i}": w for i, w in enumerate(w5)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
+             **{f"t{i}": w for i, w in enumerate(w5)}, **{f"u{i}": w for i, w in enumerate(w6)}, loss=tot, used=cnt, lo=lo, hi=hi, **{f"f{lo + i}": f for i, f in enumerate(feats)})
     dist.destroy_process_group()
 
 
@@ -120,8 +122,10 @@ def test_multi_gpu_training_and_extraction_match_single_gpu(sz, ctx, oracle, tmp
             assert np.array_equal(outs[0][f"r{i}"], outs[k][f"r{i}"])     # order (one-shot): bit-identical replicas
             assert np.array_equal(outs[0][f"s{i}"], outs[k][f"s{i}"])
             assert np.array_equal(outs[0][f"t{i}"], outs[k][f"t{i}"])
+            assert np.array_equal(outs[0][f"u{i}"], outs[k][f"u{i}"])
     for i in range(6):
-        assert np.array_equal(outs[0][f"q{i}"], outs[0][f"s{i}"])         # the two protocols add in the same order: same bits
+        assert np.array_equal(outs[0][f"q{i}"], outs[0][f"s{i}"])         # the protocols add in the same order: same bits
+        assert np.array_equal(outs[0][f"q{i}"], outs[0][f"u{i}"])         # ... also with the flag inside the packets (no flag round)
     single = sz.FeatureExtractor(ctx).extract_batch(clips)
     seen = 0
     for k in range(world):
