@@ -86,7 +86,8 @@ struct szb_ctx {
     int graph_max_rows = 1 << 30;   // largest batch whose epoch replays the captured two-step graph (SZB_GRAPH_MAX_ROWS); round 2 stopped at
                                     // 256 rows -- large batches gain little on an idle host (77.4 vs 79.0 us per batch-4096 step) but no longer
                                     // depend on the host keeping up with nine launches per 80 us (bench.py runs next to its clock sampler)
-    bool graph_peers = true;    // ... also in multi-GPU steps with the peer-memory exchange (SZB_GRAPH_PEERS=0: single GPU only)
+    bool graph_peers = false;   // ... also in multi-GPU steps with the peer-memory exchange (SZB_GRAPH_PEERS=1; the exchange step number then
+                                // lives in device memory).  Tested at world 2 (identical results, same 102 us per step): no gain, so off
     bool graphs = true;   // small-batch training epochs replay a captured two-step CUDA graph (SZB_NO_GRAPHS=1 turns it off)
     bool pdl = true;   // programmatic dependent launch between the kernels of a training step (SZB_NO_PDL=1 turns it off)
     // Launch structure of a tensor-core training step (SZB_STEP_FUSE=<bits>, default 4; 0 = eleven launches per step: batch

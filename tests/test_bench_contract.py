@@ -3,6 +3,8 @@ CPU-only: it reads the recorded lines, it does not run the bench."""
 import json
 import os
 
+import pytest
+
 from conftest import ROOT
 
 
@@ -11,8 +13,9 @@ def _line(name):
         return json.loads(f.read().strip().splitlines()[-1])
 
 
-def test_own_arm_line_has_the_contract_keys():
-    d = _line("r01_bench_n1.json")
+@pytest.mark.parametrize("name", ["r01_bench_n1.json", "r02_bench_n1.json"])
+def test_own_arm_line_has_the_contract_keys(name):
+    d = _line(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert k in d, k
@@ -31,9 +34,10 @@ def test_own_arm_line_has_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_reference_arm_line_has_the_contract_keys():
-    d = _line("r01_bench_reference_n1.json")
-    own = _line("r01_bench_n1.json")
+@pytest.mark.parametrize("rnd", ["r01", "r02"])
+def test_reference_arm_line_has_the_contract_keys(rnd):
+    d = _line(f"{rnd}_bench_reference_n1.json")
+    own = _line(f"{rnd}_bench_n1.json")
     assert d["impl"] == "reference" and d["metric"] == own["metric"] and d["unit"] == own["unit"]
     assert d["higher_is_better"] == own["higher_is_better"] and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
