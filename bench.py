@@ -288,7 +288,8 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
         def epoch(n_rows):
             N.check(N.lib.szb_net_train_epoch_dev(net._h, C.c_void_p(src.data_ptr()), C.c_void_p(labels.data_ptr()), nwin, N.ptr(perm),
                                                   n_rows, MLP_BATCH, 0.01, 0.2, 99, 0, None, C.byref(loss), C.byref(used)))
-        epoch(MLP_BATCH * 8)        # warm-up
+        epoch(nwin)                 # warm-up: one epoch of the timed size (the library captures its two-step graph and sizes its
+                                    # permutation buffer on the first epoch of a size; a training run has 60-100 epochs, main.rs:36)
         barrier()
         launches0 = ctx.launch_count
         ctx.timer_start()
@@ -364,7 +365,7 @@ def run_mlp(torch, dist, sz, N, ctx, dev, rank, world, feats, total):
             N.check(N.lib.szb_memcpy_h2d(ctx.handle, C.c_void_p(d_lab.data_ptr()), C.c_void_p(h_lab.data_ptr()), nwin * 4))
             N.check(N.lib.szb_net_train_epoch_dev(net._h, C.c_void_p(d_src.data_ptr()), C.c_void_p(d_lab.data_ptr()), nwin, N.ptr(perm),
                                                   n_rows, MLP_BATCH, 0.01, 0.2, 99, 0, None, C.byref(loss), C.byref(used)))
-        e2e_epoch(MLP_BATCH * 8)
+        e2e_epoch(nwin)
         barrier()
         t0 = time.perf_counter()
         e2e_epoch(nwin)
