@@ -57,7 +57,8 @@ struct SmemLayoutTma {
 };
 
 // Wait of a PRODUCER warp: the issuer of the MMAs shares its scheduler with four producer warps, and a warp that spins on
-// mbarrier.try_wait takes issue slots from it.  SZB_TMA_BACKOFF (ns) > 0: sleep between polls.
+// mbarrier.try_wait takes issue slots from it.  SZB_TMA_BACKOFF (ns) > 0: sleep between polls.  MEASURED: 50 and 200 ns change
+// nothing (chain of the step's eight GEMMs 75.9 / 75.8 us against 76.0 us): the polls are not what slows the MMA stream; 0 stays.
 #ifndef SZB_TMA_BACKOFF
 #define SZB_TMA_BACKOFF 0
 #endif

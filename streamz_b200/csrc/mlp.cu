@@ -572,6 +572,8 @@ __device__ __forceinline__ float p2p_grad_at(const P2pArgs& a, const float* __re
 // the peers' packets of exactly those elements and adds them in rank order (replicas stay bit-identical, and equal to the
 // other two protocols bit for bit).  Costs twice the bytes; slots alternate by step parity exactly as in the one-shot exchange
 // (a slot is rewritten two steps later, after every peer has sent the step in between, i.e. finished the update that read it).
+// A slot last written by one of the other protocols holds plain floats where this one expects flags: a false match would need a
+// gradient value whose bits equal the step counter (a denormal below 1e-38); the region starts zeroed and steps count from 1.
 __device__ __forceinline__ unsigned long long* ll_slot(const P2pArgs& a, int dst, int src, const uint32_t step) {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(a.area[dst]) +
                                                  (size_t(step & 1u) * size_t(a.world) + size_t(src)) * a.cap * sizeof(float));
