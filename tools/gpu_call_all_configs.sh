@@ -1,6 +1,6 @@
 #!/bin/bash
-# gpurun helper (1 GPU): whole GPU suite, smoke(), the default bench line and the reference arm, the other BASELINE configs,
-# then the ncu launch list of a short bench run restricted to the library's kernels.
+# gpurun helper (1 GPU): whole GPU suite, smoke(), the default bench line and the reference arm, and the other BASELINE configs
+# (c1, c4, c5).  ~5 minutes of box time.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -16,6 +16,3 @@ for c in c1 c4 c5; do
   ( time timeout 900 python bench.py --config $c ) > gpurun_out/r02_bench_${c}_n1.json 2> gpurun_out/full_bench_$c.err
   echo "bench $c rc=$?" | tee -a gpurun_out/full_summary.txt
 done
-python bench.py --no-cpu --steps 2 --warmup 3 > gpurun_out/ncu_plain_bench.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'extract_kernel|resample_kernel|gemm_|softmax|sgd_|prep_batch|downmix|train_small' -c 400 --csv --log-file gpurun_out/launches_bench_raw.csv python bench.py --no-cpu --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
-echo "launch list rc=$?" | tee -a gpurun_out/full_summary.txt
