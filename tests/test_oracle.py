@@ -18,6 +18,17 @@ def test_mel_bank_matches_torchaudio_fixture(oracle, golden):
     assert 735 <= int((mel > 0).sum()) <= 745      # ~740 non-zeros
 
 
+def test_mel_bank_matches_a_second_independent_implementation(oracle):
+    # transformers.audio_utils.mel_filter_bank is Hugging Face's own restatement of librosa's filter bank (Slaney scale, Slaney
+    # area normalisation): a second witness, beside torchaudio's, of the semantics the oracle assumes for the mel_filter crate
+    # (lib.rs:240-248).  Evaluated live (no fixture); skipped when the package cannot be imported.
+    audio_utils = pytest.importorskip("transformers.audio_utils")
+    hf = audio_utils.mel_filter_bank(num_frequency_bins=401, num_mel_filters=26, min_frequency=0.0, max_frequency=22050.0,
+                                     sampling_rate=44100, norm="slaney", mel_scale="slaney")
+    mine = oracle.mel_filterbank(dtype=np.float64)
+    assert hf.shape == (401, 26) and np.abs(hf.T - mine).max() <= 1e-12
+
+
 def test_oracle_matches_independent_golden(oracle, golden):
     for name in ("a", "b"):
         got = oracle.extract(golden[f"clip_{name}_i16"])
